@@ -1,0 +1,693 @@
+// hem_b200.cu — host orchestration + C ABI (include/hem_b200.h) of the B200-native
+// HEM Gaussian-mixture downsampler.  Kernels live in hem_kernels.cuh, bit-level
+// arithmetic in hem_math.cuh.  Build: see csrc/Makefile (nvcc, sm_100a only).
+//
+// There is no CPU fallback anywhere in this file: every entry point either runs
+// the CUDA path or returns an error.
+#include "../../include/hem_b200.h"
+#include "hem_kernels.cuh"
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace hem;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct Level {
+    int64_t n = 0;
+    DevBuf geo;    // float4[4*cap]
+    DevBuf sh;     // float[cap*Fp]
+};
+
+struct StepStats {
+    int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0;
+    double cell_size = 0, max_radius = 0;
+    double ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact
+};
+
+struct StepPairs {
+    std::vector<uint32_t> parent_idx, child;
+    std::vector<int64_t> off;
+    std::vector<float> wl, sumlw, radius;
+};
+
+enum { EV_BEGIN = 0, EV_PREP, EV_GRID, EV_GATE, EV_SUMLW, EV_MOM, EV_END, EV_COUNT };
+
+} // namespace
+
+struct hem_ctx {
+    int device = 0;
+    uint64_t seed = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    bool timing = false, keep_pairs = false;
+    double cell_scale = 1.0;
+    bool rng_base_set = false;
+    uint64_t rng_base = 0;
+    int F = 0, Fp = 0;
+    int sm_count = 148;
+
+    std::vector<Level> levels;
+    std::vector<StepStats> stats;
+    std::vector<StepPairs> pairs;
+
+    // workspace (grow-only, reused across steps and builds)
+    DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
+    DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
+    DevBuf radius, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
+    DevBuf pair_cnt, pair_off, parent_of_rank, pool, chunks, csr_child, csr_wl, sk, sv, sumlw, oflag, orank;
+    DevBuf valid, vflag, vpos, cubtmp, counters, prep, nsel, tmp_geo, tmp_sh;
+    unsigned long long* h_counters = nullptr;   // pinned
+    PrepStats* h_prep = nullptr;                // pinned
+    cudaEvent_t ev[EV_COUNT] = {};
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,       \
+                     cudaGetErrorString(e_));                                                      \
+            ctx->err = buf_;                                                                       \
+            return HEM_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define CKR(expr)                                                                                  \
+    do {                                                                                           \
+        int r_ = (expr);                                                                           \
+        if (r_ != HEM_OK) return r_;                                                               \
+    } while (0)
+
+int ensure(hem_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return HEM_OK;
+    if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return HEM_OK;
+}
+
+void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// returns a device pointer holding `bytes` from `src` (staging through `stage` if src is host memory)
+int to_device(hem_ctx* ctx, const void* src, size_t bytes, DevBuf& stage, const void** out)
+{
+    if (!src) { *out = nullptr; return HEM_OK; }
+    if (is_device_ptr(src)) { *out = src; return HEM_OK; }
+    CKR(ensure(ctx, stage, bytes));
+    CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = stage.p;
+    return HEM_OK;
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+int bits_for(uint64_t max_value)
+{
+    int b = 1;
+    while (b < 32 && (max_value >> b)) ++b;
+    return b;
+}
+
+template <class F> int cub_call(hem_ctx* ctx, F&& f)
+{
+    size_t bytes = 0;
+    CK(f((void*)nullptr, bytes));
+    CKR(ensure(ctx, ctx->cubtmp, bytes));
+    size_t have = ctx->cubtmp.cap;
+    CK(f(ctx->cubtmp.p, have));
+    return HEM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// one clustering step: levels[l] -> levels[l+1]
+// ---------------------------------------------------------------------------
+int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, float color_delta, float decay_rate,
+             uint64_t rng_base)
+{
+    cudaStream_t st = ctx->stream;
+    Level& in = ctx->levels[l];
+    Level& out = ctx->levels[l + 1];
+    StepStats& S = ctx->stats[l];
+    const int64_t n = in.n;
+    const int Fp = ctx->Fp;
+    const float pp = 1.0f / hem_reduction;
+    S = StepStats();
+    S.n_in = n;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_BEGIN], st));
+
+    if (n == 0) { out.n = 0; return HEM_OK; }
+    if (n >= (int64_t)1 << 31) { ctx->err = "more than 2^31-1 components per level is not supported"; return HEM_ERR_INVALID; }
+
+    const float4* geo = in.geo.as<float4>();
+    const float* sh = in.sh.as<float>();
+
+    // ---- S1 prep --------------------------------------------------------------------------
+    CKR(ensure(ctx, ctx->radius, n * 4));
+    CKR(ensure(ctx, ctx->pflag, n * 4));
+    CKR(ensure(ctx, ctx->prank, n * 4));
+    CKR(ensure(ctx, ctx->prep, sizeof(PrepStats)));
+    CKR(ensure(ctx, ctx->counters, C_COUNT * sizeof(unsigned long long)));
+    {
+        PrepStats init;
+        for (int a = 0; a < 3; ++a) { init.bbmin[a] = INT_MAX; init.bbmax[a] = INT_MIN; }
+        init.max_radius_bits = 0; init.n_radius = 0; init.sum_radius = 0.0;
+        *ctx->h_prep = init;
+        CK(cudaMemcpyAsync(ctx->prep.p, ctx->h_prep, sizeof(PrepStats), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long), st));
+    }
+    k_prep<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, distance_delta, ctx->radius.as<float>(),
+                                                ctx->pflag.as<uint32_t>(), ctx->prep.as<PrepStats>());
+    CK(cudaGetLastError());
+    CKR(cub_call(ctx, [&](void* t, size_t& b) {
+        return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
+    }));
+    // parent count = prank[n-1] + pflag[n-1]
+    uint32_t h_tail[2];
+    CK(cudaMemcpyAsync(ctx->h_prep, ctx->prep.p, sizeof(PrepStats), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->prank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_counters[9], ctx->pflag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));                                      // sync A
+    memcpy(&h_tail[0], &ctx->h_counters[8], 4);
+    memcpy(&h_tail[1], &ctx->h_counters[9], 4);
+    const int64_t np = (int64_t)h_tail[0] + h_tail[1];
+    const PrepStats ps = *ctx->h_prep;
+    S.n_parents = np;
+    float max_radius = 0.0f;
+    memcpy(&max_radius, &ps.max_radius_bits, 4);
+    S.max_radius = max_radius;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_PREP], st));
+
+    // next level store: upper bound n + np rows (a NaN-radius parent is both a merged row and an orphan)
+    const int64_t cap_rows = n + np;
+    CKR(ensure(ctx, out.geo, (size_t)cap_rows * 64));
+    CKR(ensure(ctx, out.sh, (size_t)cap_rows * std::max(Fp, 1) * 4));
+    CKR(ensure(ctx, ctx->valid, cap_rows));
+    CKR(ensure(ctx, ctx->sumlw, n * 4));
+    CK(cudaMemsetAsync(ctx->sumlw.p, 0, n * 4, st));
+
+    int64_t P = 0;
+    const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
+    if (have_pairs) {
+        // ---- S2 grid --------------------------------------------------------------------------
+        GridP g;
+        {
+            float bmin[3], bmax[3];
+            for (int a = 0; a < 3; ++a) {
+                bmin[a] = ps.bbmin[a] == INT_MAX ? 0.0f : ord2f(ps.bbmin[a]);
+                bmax[a] = ps.bbmax[a] == INT_MIN ? 0.0f : ord2f(ps.bbmax[a]);
+                if (!std::isfinite(bmin[a])) bmin[a] = -FLT_MAX;
+                if (!std::isfinite(bmax[a])) bmax[a] = FLT_MAX;
+            }
+            double h = ps.n_radius ? ctx->cell_scale * (ps.sum_radius / (double)ps.n_radius) : 1.0;
+            if (!(h > 0)) h = 1.0;
+            const double max_cells = 1 << 24;
+            double ext[3];
+            for (int a = 0; a < 3; ++a) ext[a] = std::max(0.0, (double)bmax[a] - (double)bmin[a]);
+            for (int it = 0; it < 64; ++it) {
+                double cells = 1;
+                bool too_long = false;
+                for (int a = 0; a < 3; ++a) {
+                    double d = std::floor(ext[a] / h) + 1;
+                    if (d > 2047) too_long = true;
+                    cells *= d;
+                }
+                if (cells <= max_cells && !too_long) break;
+                h *= 1.26;
+            }
+            g.ox = bmin[0]; g.oy = bmin[1]; g.oz = bmin[2];
+            g.inv_h = (float)(1.0 / h);
+            g.gx = (int)std::min(2047.0, std::floor(ext[0] / h)) + 1;
+            g.gy = (int)std::min(2047.0, std::floor(ext[1] / h)) + 1;
+            g.gz = (int)std::min(2047.0, std::floor(ext[2] / h)) + 1;
+            S.cell_size = h;
+        }
+        const uint32_t ncell = (uint32_t)g.gx * g.gy * g.gz;
+        S.grid_cells = ncell;
+        CKR(ensure(ctx, ctx->key, n * 4)); CKR(ensure(ctx, ctx->key2, n * 4));
+        CKR(ensure(ctx, ctx->val, n * 4)); CKR(ensure(ctx, ctx->val2, n * 4));
+        CKR(ensure(ctx, ctx->sp0, n * 16)); CKR(ensure(ctx, ctx->sp1, n * 16));
+        CKR(ensure(ctx, ctx->sp2, n * 16)); CKR(ensure(ctx, ctx->sp3, n * 16));
+        CKR(ensure(ctx, ctx->sflag, n));
+        CKR(ensure(ctx, ctx->cell_start, ((size_t)ncell + 1) * 4));
+        CKR(ensure(ctx, ctx->psorted, np * 4));
+        CKR(ensure(ctx, ctx->nsel, 8));
+        k_cellkey<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, g, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
+        CK(cudaGetLastError());
+        const int kbits = bits_for(ncell - 1);
+        CKR(cub_call(ctx, [&](void* t, size_t& b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, ctx->key.as<uint32_t>(), ctx->key2.as<uint32_t>(),
+                                                   ctx->val.as<uint32_t>(), ctx->val2.as<uint32_t>(), (int)n, 0, kbits, st);
+        }));
+        k_sorted_gather<<<blocks_for(n, 256), 256, 0, st>>>(geo, ctx->key2.as<uint32_t>(), ctx->val2.as<uint32_t>(), n,
+                                                             ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
+                                                             ctx->sp2.as<float4>(), ctx->sp3.as<float4>(),
+                                                             ctx->sflag.as<uint8_t>(), ctx->cell_start.as<uint32_t>());
+        CK(cudaGetLastError());
+        CKR(cub_call(ctx, [&](void* t, size_t& b) {
+            return cub::DeviceSelect::Flagged(t, b, thrust::counting_iterator<uint32_t>(0), ctx->sflag.as<uint8_t>(),
+                                              ctx->psorted.as<uint32_t>(), ctx->nsel.as<uint32_t>(), (int)n, st);
+        }));
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
+
+        // ---- S3 gate ----------------------------------------------------------------------------
+        CKR(ensure(ctx, ctx->pair_cnt, (np + 1) * 4));
+        CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
+        size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n, 1 << 16));
+        for (int attempt = 0; attempt < 8; ++attempt) {
+            const size_t chunk_cap = (size_t)np + pool_cap / (GATE_OUTCAP - 32) + 16;
+            CKR(ensure(ctx, ctx->pool, pool_cap * 8));
+            CKR(ensure(ctx, ctx->chunks, chunk_cap * 16));
+            CK(cudaMemsetAsync(ctx->pair_cnt.p, 0, (np + 1) * 4, st));
+            CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(unsigned long long), st));
+            GateArgs A;
+            A.sp0 = ctx->sp0.as<float4>(); A.sp1 = ctx->sp1.as<float4>(); A.sp2 = ctx->sp2.as<float4>();
+            A.sp3 = ctx->sp3.as<float4>(); A.cell_start = ctx->cell_start.as<uint32_t>();
+            A.psorted = ctx->psorted.as<uint32_t>(); A.prank = ctx->prank.as<uint32_t>();
+            A.radius = ctx->radius.as<float>(); A.geo = geo; A.g = g; A.np = (int)np;
+            A.cthr = color_delta * color_delta * 0.5f;           // mixture.cpp:123
+            A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
+            A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
+            A.pair_cnt = ctx->pair_cnt.as<uint32_t>();
+            A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
+            A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
+            A.counters = ctx->counters.as<unsigned long long>();
+            k_gate<<<blocks_for(np, GATE_WARPS), GATE_WARPS * 32, 0, st>>>(A);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));                              // sync B
+            if (ctx->h_counters[C_POOL] <= pool_cap && ctx->h_counters[C_CHUNK] <= chunk_cap) break;
+            pool_cap = (size_t)ctx->h_counters[C_POOL] + (size_t)ctx->h_counters[C_POOL] / 4 + 1024;
+            if (attempt == 7) { ctx->err = "pair pool overflow persisted"; return HEM_ERR_STATE; }
+        }
+        P = (int64_t)ctx->h_counters[C_POOL];
+        const unsigned long long nchunks = ctx->h_counters[C_CHUNK];
+        if (P >= (int64_t)1 << 32) { ctx->err = "more than 2^32-1 accepted pairs per level is not supported"; return HEM_ERR_INVALID; }
+        S.n_pairs = P;
+        CKR(cub_call(ctx, [&](void* t, size_t& b) {
+            return cub::DeviceScan::ExclusiveSum(t, b, ctx->pair_cnt.as<uint32_t>(), ctx->pair_off.as<uint32_t>(),
+                                                 (int)(np + 1), st);
+        }));
+        CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
+        CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
+        if (nchunks > 0) {
+            k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
+                ctx->chunks.as<uint4>(), nchunks, ctx->pool.as<uint2>(), ctx->pair_off.as<uint32_t>(),
+                ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
+            CK(cudaGetLastError());
+        }
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
+
+        // ---- per-child normaliser ------------------------------------------------------------------
+        if (P > 0) {
+            CKR(ensure(ctx, ctx->sk, P * 4));
+            CKR(ensure(ctx, ctx->sv, P * 4));
+            const int cbits = bits_for((uint64_t)n - 1);
+            CKR(cub_call(ctx, [&](void* t, size_t& b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, ctx->csr_child.as<uint32_t>(), ctx->sk.as<uint32_t>(),
+                                                       ctx->csr_wl.as<float>(), ctx->sv.as<float>(), (int)P, 0, cbits, st);
+            }));
+            k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P,
+                                                          ctx->sumlw.as<float>());
+            CK(cudaGetLastError());
+        }
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+
+        // ---- S4 moments -------------------------------------------------------------------------------
+        MomArgs M;
+        M.geo = geo; M.sh = sh; M.Fp = Fp; M.psorted = ctx->psorted.as<uint32_t>(); M.sp0 = ctx->sp0.as<float4>();
+        M.prank = ctx->prank.as<uint32_t>(); M.np = (int)np; M.pair_off = ctx->pair_off.as<uint32_t>();
+        M.csr_child = ctx->csr_child.as<uint32_t>(); M.csr_wl = ctx->csr_wl.as<float>(); M.sumlw = ctx->sumlw.as<float>();
+        M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>(); M.valid = ctx->valid.as<uint8_t>();
+        M.seed = ctx->seed; M.rng_base = rng_base; M.pp = pp; M.counters = ctx->counters.as<unsigned long long>();
+        k_moments<<<blocks_for(np, MOM_WARPS), MOM_WARPS * 32, 0, st>>>(M);
+        CK(cudaGetLastError());
+    } else if (ctx->timing) {
+        CK(cudaEventRecord(ctx->ev[EV_GRID], st));
+        CK(cudaEventRecord(ctx->ev[EV_GATE], st));
+        CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+    }
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
+
+    // ---- S5 orphans + filter ---------------------------------------------------------------------------
+    CKR(ensure(ctx, ctx->oflag, n * 4));
+    CKR(ensure(ctx, ctx->orank, n * 4));
+    k_orphan_flag<<<blocks_for(n, 256), 256, 0, st>>>(ctx->sumlw.as<float>(), n, ctx->oflag.as<uint32_t>());
+    CK(cudaGetLastError());
+    CKR(cub_call(ctx, [&](void* t, size_t& b) {
+        return cub::DeviceScan::ExclusiveSum(t, b, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(), (int)n, st);
+    }));
+    k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(),
+                                                   (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>(),
+                                                   ctx->valid.as<uint8_t>(), ctx->seed, rng_base, pp,
+                                                   ctx->counters.as<unsigned long long>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->orank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_counters[9], ctx->oflag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));                                      // sync C
+    uint32_t ot[2];
+    memcpy(&ot[0], &ctx->h_counters[8], 4);
+    memcpy(&ot[1], &ctx->h_counters[9], 4);
+    const int64_t norph = (int64_t)ot[0] + ot[1];
+    const int64_t npre = np + norph;
+    const int64_t ninvalid = (int64_t)ctx->h_counters[C_INVALID];
+    S.n_orphans = norph;
+    S.n_dropped = ninvalid;
+    out.n = npre;
+    if (ninvalid > 0) {
+        // rare path: erase invalid outputs keeping order (mixture.cpp:262-282)
+        CKR(ensure(ctx, ctx->vflag, npre * 4));
+        CKR(ensure(ctx, ctx->vpos, npre * 4));
+        CKR(ensure(ctx, ctx->tmp_geo, (size_t)npre * 64));
+        CKR(ensure(ctx, ctx->tmp_sh, (size_t)npre * std::max(Fp, 1) * 4));
+        k_valid_flag<<<blocks_for(npre, 256), 256, 0, st>>>(ctx->valid.as<uint8_t>(), npre, ctx->vflag.as<uint32_t>());
+        CK(cudaGetLastError());
+        CKR(cub_call(ctx, [&](void* t, size_t& b) {
+            return cub::DeviceScan::ExclusiveSum(t, b, ctx->vflag.as<uint32_t>(), ctx->vpos.as<uint32_t>(), (int)npre, st);
+        }));
+        k_compact_rows<<<blocks_for(npre * 32, 256), 256, 0, st>>>(out.geo.as<float4>(), out.sh.as<float>(), Fp, npre,
+                                                                    ctx->valid.as<uint8_t>(), ctx->vpos.as<uint32_t>(),
+                                                                    ctx->tmp_geo.as<float4>(), ctx->tmp_sh.as<float>());
+        CK(cudaGetLastError());
+        const int64_t nout = npre - ninvalid;
+        CK(cudaMemcpyAsync(out.geo.p, ctx->tmp_geo.p, (size_t)nout * 64, cudaMemcpyDeviceToDevice, st));
+        if (Fp > 0) CK(cudaMemcpyAsync(out.sh.p, ctx->tmp_sh.p, (size_t)nout * Fp * 4, cudaMemcpyDeviceToDevice, st));
+        out.n = nout;
+    }
+    S.n_out = out.n;
+    if (ctx->timing) {
+        CK(cudaEventRecord(ctx->ev[EV_END], st));
+        CK(cudaEventSynchronize(ctx->ev[EV_END]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_BEGIN], ctx->ev[EV_END]); S.ms[0] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_BEGIN], ctx->ev[EV_PREP]); S.ms[1] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_PREP], ctx->ev[EV_GRID]); S.ms[2] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_GRID], ctx->ev[EV_GATE]); S.ms[3] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_GATE], ctx->ev[EV_SUMLW]); S.ms[4] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_SUMLW], ctx->ev[EV_MOM]); S.ms[5] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_MOM], ctx->ev[EV_END]); S.ms[6] = ms;
+    }
+
+    if (ctx->keep_pairs) {
+        StepPairs& K = ctx->pairs[l];
+        K = StepPairs();
+        K.sumlw.resize(n);
+        CK(cudaMemcpyAsync(K.sumlw.data(), ctx->sumlw.p, n * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> pflag(n);
+        std::vector<float> rad(n);
+        CK(cudaMemcpyAsync(pflag.data(), ctx->pflag.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rad.data(), ctx->radius.p, n * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> off32(np + 1, 0);
+        K.child.resize(P);
+        K.wl.resize(P);
+        if (have_pairs) {
+            CK(cudaMemcpyAsync(off32.data(), ctx->pair_off.p, (np + 1) * 4, cudaMemcpyDeviceToHost, st));
+            if (P > 0) {
+                CK(cudaMemcpyAsync(K.child.data(), ctx->csr_child.p, P * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(K.wl.data(), ctx->csr_wl.p, P * 4, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        CK(cudaStreamSynchronize(st));
+        K.off.assign(off32.begin(), off32.end());
+        for (int64_t i = 0; i < n; ++i)
+            if (pflag[i]) { K.parent_idx.push_back((uint32_t)i); K.radius.push_back(rad[i]); }
+    }
+    return HEM_OK;
+}
+
+} // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int hem_version(void) { return 1000; }
+
+const char* hem_last_error(const hem_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+hem_ctx* hem_create(int device, uint64_t seed)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_error = "cudaGetDeviceProperties failed"; return nullptr; }
+    if (prop.major != 10) {
+        g_create_error = "libhem_b200 is built for sm_100a (Blackwell B200) only; device is sm_" +
+                         std::to_string(prop.major) + std::to_string(prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return nullptr; }
+    hem_ctx* ctx = new hem_ctx();
+    ctx->device = device;
+    ctx->seed = seed;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_prep, sizeof(PrepStats)) != cudaSuccess) {
+        g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return nullptr;
+    }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    return ctx;
+}
+
+void hem_destroy(hem_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (Level& L : ctx->levels) { release(L.geo); release(L.sh); }
+    DevBuf* all[] = { &ctx->in_xyz, &ctx->in_col, &ctx->in_op, &ctx->in_cov, &ctx->in_sh, &ctx->in_w, &ctx->in_mask,
+                      &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
+                      &ctx->radius, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
+                      &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
+                      &ctx->pair_cnt, &ctx->pair_off, &ctx->parent_of_rank, &ctx->pool, &ctx->chunks, &ctx->csr_child,
+                      &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->sumlw, &ctx->oflag, &ctx->orank, &ctx->valid, &ctx->vflag,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->counters, &ctx->prep, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh };
+    for (DevBuf* b : all) release(*b);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_prep) cudaFreeHost(ctx->h_prep);
+    for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int hem_set_stream(hem_ctx* ctx, void* stream)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return HEM_OK;
+}
+
+int hem_set_option(hem_ctx* ctx, const char* name, double value)
+{
+    if (!ctx || !name) return HEM_ERR_INVALID;
+    std::string k(name);
+    if (k == "timing") ctx->timing = value != 0;
+    else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
+    else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
+    else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
+    else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }
+    return HEM_OK;
+}
+
+int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const float* opacity, const float* cov6,
+                      const float* sh, const float* weight, int64_t n, int32_t sh_floats, uint32_t cluster_level,
+                      float hem_reduction, float distance_delta, float color_delta, float decay_rate,
+                      const uint8_t* level0_parent_mask)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    ctx->err.clear();
+    if (n < 0 || sh_floats < 0 || sh_floats > 64) { ctx->err = "n must be >= 0 and 0 <= sh_floats <= 64"; return HEM_ERR_INVALID; }
+    if (n > 0 && (!xyz || !color || !opacity || !cov6 || (sh_floats > 0 && !sh))) { ctx->err = "null input array"; return HEM_ERR_INVALID; }
+    if (!(hem_reduction > 0)) { ctx->err = "hem_reduction must be > 0"; return HEM_ERR_INVALID; }
+    if (cluster_level > 64) { ctx->err = "cluster_level > 64"; return HEM_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->F = sh_floats;
+    ctx->Fp = (sh_floats + 3) / 4 * 4;
+    const int Fp = ctx->Fp;
+    if (ctx->levels.size() < (size_t)cluster_level + 1) ctx->levels.resize((size_t)cluster_level + 1);
+    for (Level& L : ctx->levels) L.n = 0;
+    ctx->stats.assign(cluster_level, StepStats());
+    ctx->pairs.assign(ctx->keep_pairs ? cluster_level : 0, StepPairs());
+
+    // level 0 = the input (Mixture::initMixture, mixture.cpp:287-333)
+    Level& L0 = ctx->levels[0];
+    L0.n = n;
+    if (n > 0) {
+        const void *dx, *dc, *dop, *dcv, *dsh, *dw, *dm;
+        CKR(to_device(ctx, xyz, (size_t)n * 12, ctx->in_xyz, &dx));
+        CKR(to_device(ctx, color, (size_t)n * 12, ctx->in_col, &dc));
+        CKR(to_device(ctx, opacity, (size_t)n * 4, ctx->in_op, &dop));
+        CKR(to_device(ctx, cov6, (size_t)n * 24, ctx->in_cov, &dcv));
+        CKR(to_device(ctx, sh_floats ? sh : nullptr, (size_t)n * sh_floats * 4, ctx->in_sh, &dsh));
+        CKR(to_device(ctx, weight, (size_t)n * 4, ctx->in_w, &dw));
+        CKR(to_device(ctx, level0_parent_mask, (size_t)n, ctx->in_mask, &dm));
+        CKR(ensure(ctx, L0.geo, (size_t)n * 64));
+        CKR(ensure(ctx, L0.sh, (size_t)n * std::max(Fp, 1) * 4));
+        k_import<<<blocks_for(n, 256), 256, 0, st>>>((const float*)dx, (const float*)dc, (const float*)dop,
+                                                      (const float*)dcv, (const float*)dw, (const uint8_t*)dm,
+                                                      L0.geo.as<float4>(), n, ctx->seed, 1.0f / hem_reduction);
+        CK(cudaGetLastError());
+        if (Fp > 0) {
+            k_pad_sh<<<blocks_for(n * Fp, 256), 256, 0, st>>>((const float*)dsh, L0.sh.as<float>(), n, sh_floats, Fp);
+            CK(cudaGetLastError());
+        }
+    }
+    uint64_t base = ctx->rng_base_set ? ctx->rng_base : (uint64_t)n;
+    for (uint32_t l = 0; l < cluster_level; ++l) {
+        CKR(run_step(ctx, (int)l, hem_reduction, distance_delta, color_delta, decay_rate, base));
+        base += (uint64_t)(ctx->stats[l].n_parents + ctx->stats[l].n_orphans);    // pre-filter size, mixture.cpp:257-259
+    }
+    CK(cudaStreamSynchronize(st));
+    return HEM_OK;
+}
+
+int hem_num_levels(const hem_ctx* ctx) { return ctx ? (int)ctx->stats.size() + (ctx->levels.empty() ? 0 : 1) : 0; }
+
+int64_t hem_level_size(const hem_ctx* ctx, int level)
+{
+    if (!ctx || level < 0 || level > (int)ctx->stats.size() || (size_t)level >= ctx->levels.size()) return -1;
+    return ctx->levels[level].n;
+}
+
+static int from_device(hem_ctx* ctx, void* dst, size_t bytes, DevBuf& stage, void** dev_out, bool* staged)
+{
+    *staged = false;
+    if (!dst) { *dev_out = nullptr; return HEM_OK; }
+    if (is_device_ptr(dst)) { *dev_out = dst; return HEM_OK; }
+    CKR(ensure(ctx, stage, bytes));
+    *dev_out = stage.p;
+    *staged = true;
+    return HEM_OK;
+}
+
+int hem_level_copy(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
+                   float* weight, uint8_t* is_parent)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    if (level < 0 || level > (int)ctx->stats.size() || (size_t)level >= ctx->levels.size()) { ctx->err = "level not built"; return HEM_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Level& L = ctx->levels[level];
+    const int64_t n = L.n;
+    if (n == 0) return HEM_OK;
+    const int F = ctx->F, Fp = ctx->Fp;
+    void *dx, *dc, *dop, *dcv, *dsh, *dw, *df;
+    bool sx, sc, sop, scv, ssh, sw, sf;
+    CKR(from_device(ctx, xyz, (size_t)n * 12, ctx->out_a, &dx, &sx));
+    CKR(from_device(ctx, color, (size_t)n * 12, ctx->out_b, &dc, &sc));
+    CKR(from_device(ctx, opacity, (size_t)n * 4, ctx->out_c, &dop, &sop));
+    CKR(from_device(ctx, cov6, (size_t)n * 24, ctx->out_d, &dcv, &scv));
+    CKR(from_device(ctx, F ? sh : nullptr, (size_t)n * F * 4, ctx->out_e, &dsh, &ssh));
+    CKR(from_device(ctx, weight, (size_t)n * 4, ctx->out_f, &dw, &sw));
+    CKR(from_device(ctx, is_parent, (size_t)n, ctx->out_g, &df, &sf));
+    k_export<<<blocks_for(n, 256), 256, 0, st>>>(L.geo.as<float4>(), n, (float*)dx, (float*)dc, (float*)dop, (float*)dcv,
+                                                  (float*)dw, (uint8_t*)df);
+    CK(cudaGetLastError());
+    if (dsh) {
+        k_unpad_sh<<<blocks_for(n * F, 256), 256, 0, st>>>(L.sh.as<float>(), (float*)dsh, n, F, Fp);
+        CK(cudaGetLastError());
+    }
+    if (sx) CK(cudaMemcpyAsync(xyz, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    if (sc) CK(cudaMemcpyAsync(color, dc, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    if (sop) CK(cudaMemcpyAsync(opacity, dop, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (scv) CK(cudaMemcpyAsync(cov6, dcv, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    if (ssh) CK(cudaMemcpyAsync(sh, dsh, (size_t)n * F * 4, cudaMemcpyDeviceToHost, st));
+    if (sw) CK(cudaMemcpyAsync(weight, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (sf) CK(cudaMemcpyAsync(is_parent, df, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return HEM_OK;
+}
+
+int hem_step_stats(const hem_ctx* ctx, int step, double* out)
+{
+    if (!ctx || !out || step < 0 || step >= (int)ctx->stats.size()) return HEM_ERR_INVALID;
+    const StepStats& S = ctx->stats[step];
+    out[0] = (double)S.n_in; out[1] = (double)S.n_parents; out[2] = (double)S.n_pairs; out[3] = (double)S.n_orphans;
+    out[4] = (double)S.n_dropped; out[5] = (double)S.n_out; out[6] = (double)S.grid_cells; out[7] = S.cell_size;
+    out[8] = S.max_radius;
+    for (int i = 0; i < 7; ++i) out[9 + i] = S.ms[i];
+    return HEM_OK;
+}
+
+int hem_step_pairs(hem_ctx* ctx, int step, uint32_t* parent_idx, int64_t* off, uint32_t* child, float* wl,
+                   float* sumlw, float* radius)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    if (step < 0 || step >= (int)ctx->pairs.size()) { ctx->err = "pairs not kept (set option keep_pairs before building)"; return HEM_ERR_STATE; }
+    const StepPairs& K = ctx->pairs[step];
+    if (parent_idx) memcpy(parent_idx, K.parent_idx.data(), K.parent_idx.size() * 4);
+    if (off) memcpy(off, K.off.data(), K.off.size() * 8);
+    if (child) memcpy(child, K.child.data(), K.child.size() * 4);
+    if (wl) memcpy(wl, K.wl.data(), K.wl.size() * 4);
+    if (sumlw) memcpy(sumlw, K.sumlw.data(), K.sumlw.size() * 4);
+    if (radius) memcpy(radius, K.radius.data(), K.radius.size() * 4);
+    return HEM_OK;
+}
+
+int hem_nccl_unique_id(uint8_t* id_out)
+{
+    (void)id_out;
+    return HEM_ERR_NCCL;
+}
+
+int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world)
+{
+    (void)id; (void)rank; (void)world;
+    if (ctx) ctx->err = "multi-GPU communicator not available in this build";
+    return HEM_ERR_NCCL;
+}
+
+} // extern "C"

@@ -1,0 +1,182 @@
+"""Tensor/array-level API over the C ABI: build HEM pyramids on a B200.
+
+``HemContext.build`` accepts numpy arrays (host memory; copied H2D inside the
+call) or torch CUDA tensors (used in place through their data pointers) and
+returns per-level arrays in the reference's attribute layout
+(reference src/cpp_ext/src/mixturelevel.cpp:30-70).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+
+STAT_NAMES = ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out", "grid_cells", "cell_size",
+              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact")
+
+
+@dataclass
+class HemParams:
+    """Mirror of the reference's GaussianMixtureParams (src/params/merge_parameters.py:4-10)."""
+    hem_reduction: float = 3.0
+    distance_delta: float = 3.0
+    color_delta: float = 2.5
+    decay_rate: float = 1.0
+    cluster_level: int = 3
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    """(pointer, keepalive) of a numpy array or torch tensor, None passes through."""
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        if not x.is_contiguous():
+            x = x.contiguous()
+        return C.c_void_p(x.data_ptr()), x
+    a = np.ascontiguousarray(x)
+    return C.c_void_p(a.ctypes.data), a
+
+
+class HemContext:
+    """One context per GPU (``hem_create`` / ``hem_destroy``)."""
+
+    def __init__(self, device: int = 0, seed: int = 0):
+        self._lib = _capi.load()
+        self._h = self._lib.hem_create(int(device), int(seed))
+        if not self._h:
+            msg = self._lib.hem_last_error(None)
+            raise _capi.HemError(-3, msg.decode() if msg else "hem_create failed")
+        self.device = device
+        self.sh_floats = 0
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, code: int):
+        if code != 0:
+            msg = self._lib.hem_last_error(self._h)
+            raise _capi.HemError(code, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name: str, value: float):
+        self._check(self._lib.hem_set_option(self._h, name.encode(), float(value)))
+
+    def set_stream(self, stream_handle: int | None):
+        self._check(self._lib.hem_set_stream(self._h, C.c_void_p(stream_handle or 0)))
+
+    # -- the hot path ----------------------------------------------------------
+    def build(self, xyz, colors, opacity, cov6, sh, cluster_level: int, hem_reduction: float = 3.0,
+              distance_delta: float = 3.0, color_delta: float = 2.5, decay_rate: float = 1.0,
+              weight=None, parent_mask=None) -> int:
+        """Run ``cluster_level`` HEM steps (reference MixtureCreator.CreateMixture,
+        src/cpp_ext/mixture_wrapper.cpp:10-18).  Returns the number of levels held
+        (cluster_level + 1, level 0 = input)."""
+        n = int(xyz.shape[0])
+        F = int(sh.shape[1]) if sh is not None and len(sh.shape) == 2 else 0
+        if not _is_torch(xyz):
+            xyz, colors, opacity, cov6 = (np.ascontiguousarray(a, dtype=np.float32) for a in (xyz, colors, opacity, cov6))
+            sh = None if F == 0 else np.ascontiguousarray(sh, dtype=np.float32)
+            weight = None if weight is None else np.ascontiguousarray(weight, dtype=np.float32)
+            parent_mask = None if parent_mask is None else np.ascontiguousarray(parent_mask, dtype=np.uint8)
+        keep = []
+        ptrs = []
+        for a in (xyz, colors, opacity, cov6, sh if F else None, weight):
+            p, k = _ptr(a)
+            ptrs.append(p)
+            keep.append(k)
+        pm, k = _ptr(parent_mask)
+        keep.append(k)
+        self.sh_floats = F
+        self._check(self._lib.hem_build_pyramid(self._h, *ptrs, n, F, int(cluster_level), float(hem_reduction),
+                                                float(distance_delta), float(color_delta), float(decay_rate), pm))
+        return self.num_levels
+
+    @property
+    def num_levels(self) -> int:
+        return int(self._lib.hem_num_levels(self._h))
+
+    def level_size(self, level: int) -> int:
+        n = int(self._lib.hem_level_size(self._h, level))
+        if n < 0:
+            raise _capi.HemError(-4, f"level {level} not built")
+        return n
+
+    def level(self, level: int, with_internal: bool = False) -> dict:
+        """One level as host numpy arrays (reference CreatePythonLists layout)."""
+        n, F = self.level_size(level), self.sh_floats
+        out = dict(xyz=np.empty((n, 3), np.float32), colors=np.empty((n, 3), np.float32),
+                   opacity=np.empty(n, np.float32), cov6=np.empty((n, 6), np.float32),
+                   sh=np.empty((n, F), np.float32))
+        w = f = None
+        if with_internal:
+            out["weight"] = np.empty(n, np.float32)
+            out["is_parent"] = np.empty(n, np.uint8)
+            w, f = C.c_void_p(out["weight"].ctypes.data), C.c_void_p(out["is_parent"].ctypes.data)
+        self._check(self._lib.hem_level_copy(
+            self._h, level, C.c_void_p(out["xyz"].ctypes.data), C.c_void_p(out["colors"].ctypes.data),
+            C.c_void_p(out["opacity"].ctypes.data), C.c_void_p(out["cov6"].ctypes.data),
+            C.c_void_p(out["sh"].ctypes.data) if F else None, w, f))
+        return out
+
+    def level_torch(self, level: int, with_internal: bool = False) -> dict:
+        """One level as torch CUDA tensors (device-to-device, no host staging)."""
+        import torch
+        n, F = self.level_size(level), self.sh_floats
+        dev = torch.device("cuda", self.device)
+        out = dict(xyz=torch.empty((n, 3), dtype=torch.float32, device=dev),
+                   colors=torch.empty((n, 3), dtype=torch.float32, device=dev),
+                   opacity=torch.empty(n, dtype=torch.float32, device=dev),
+                   cov6=torch.empty((n, 6), dtype=torch.float32, device=dev),
+                   sh=torch.empty((n, F), dtype=torch.float32, device=dev))
+        w = f = None
+        if with_internal:
+            out["weight"] = torch.empty(n, dtype=torch.float32, device=dev)
+            out["is_parent"] = torch.empty(n, dtype=torch.uint8, device=dev)
+            w, f = C.c_void_p(out["weight"].data_ptr()), C.c_void_p(out["is_parent"].data_ptr())
+        self._check(self._lib.hem_level_copy(
+            self._h, level, C.c_void_p(out["xyz"].data_ptr()), C.c_void_p(out["colors"].data_ptr()),
+            C.c_void_p(out["opacity"].data_ptr()), C.c_void_p(out["cov6"].data_ptr()),
+            C.c_void_p(out["sh"].data_ptr()) if F and n else None, w, f))
+        return out
+
+    def step_stats(self, step: int) -> dict:
+        buf = (C.c_double * _capi.STEP_STATS_LEN)()
+        self._check(self._lib.hem_step_stats(self._h, step, buf))
+        d = dict(zip(STAT_NAMES, list(buf)))
+        for k in STAT_NAMES[:7]:
+            d[k] = int(d[k])
+        return d
+
+    def step_pairs(self, step: int) -> dict:
+        """White-box child lists of a step (needs option keep_pairs=1 before build)."""
+        s = self.step_stats(step)
+        npar, P, n = s["n_parents"], s["n_pairs"], s["n_in"]
+        out = dict(parent_idx=np.zeros(npar, np.uint32), off=np.zeros(npar + 1, np.int64),
+                   child=np.zeros(P, np.uint32), wl=np.zeros(P, np.float32), sumlw=np.zeros(n, np.float32),
+                   radius=np.zeros(npar, np.float32))
+        self._check(self._lib.hem_step_pairs(
+            self._h, step, out["parent_idx"].ctypes.data_as(_capi._u32), out["off"].ctypes.data_as(_capi._i64),
+            out["child"].ctypes.data_as(_capi._u32), out["wl"].ctypes.data_as(_capi._f),
+            out["sumlw"].ctypes.data_as(_capi._f), out["radius"].ctypes.data_as(_capi._f)))
+        return out

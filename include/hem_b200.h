@@ -1,0 +1,144 @@
+/* hem_b200.h — C ABI of libhem_b200.so, the B200-native (sm_100a) replacement
+ * for the hot path of erikszasz/GaussianSplattingRegistration: the hierarchical
+ * EM (HEM) Gaussian-mixture downsampler of src/cpp_ext.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference repository root).  Plain pointers and sizes only; no
+ * exceptions cross the boundary (0 = success, negative = error, message via
+ * hem_last_error).  Data pointers may be HOST or DEVICE pointers (detected with
+ * cudaPointerGetAttributes); the caller owns every buffer it passes; the
+ * context owns all device memory it allocates.
+ *
+ * Reference call surface replaced (pybind11 module `mixture_bind`,
+ * src/cpp_ext/mixture_bind.cpp:11-60):
+ *   MixtureLevel.CreateMixtureLevel(xyz, colors, opacities, covariance, features)
+ *       src/cpp_ext/src/mixturelevel.cpp:14-28       -> the five arrays of hem_build_pyramid
+ *   MixtureCreator.CreateMixture(clusterLevel, hemReduction, distanceDelta, colorDelta, decayRate, level)
+ *       src/cpp_ext/mixture_wrapper.cpp:10-18         -> hem_build_pyramid
+ *   MixtureLevel.CreatePythonLists(level)
+ *       src/cpp_ext/src/mixturelevel.cpp:30-70        -> hem_level_size + hem_level_copy
+ */
+#ifndef HEM_B200_H
+#define HEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hem_ctx hem_ctx;
+
+/* error codes */
+#define HEM_OK               0
+#define HEM_ERR_INVALID     -1   /* bad argument */
+#define HEM_ERR_CUDA        -2   /* CUDA runtime failure (message holds the CUDA error string) */
+#define HEM_ERR_NO_DEVICE   -3   /* no usable sm_100 device */
+#define HEM_ERR_STATE       -4   /* call sequence error (e.g. level not built) */
+#define HEM_ERR_NCCL        -5   /* NCCL failure / NCCL not loadable */
+
+/* Create a context on CUDA device `device` (one context per GPU, one process
+ * per GPU in multi-GPU runs).  `seed` keys the counter-based parent-selection
+ * RNG that stands in for the reference's unseeded libc generator
+ * (src/cpp_ext/include/base.hpp:44-56).  Returns NULL on failure; the reason is
+ * then available from hem_last_error(NULL). */
+hem_ctx* hem_create(int device, uint64_t seed);
+
+/* Destroy the context and free every device allocation it owns.  (The
+ * reference leaks its whole Mixture per call, mixture_wrapper.cpp:11.) */
+void hem_destroy(hem_ctx* ctx);
+
+/* Last error message of `ctx` (or of the failed hem_create when ctx == NULL). */
+const char* hem_last_error(const hem_ctx* ctx);
+
+/* Run on `stream` (a cudaStream_t) instead of the context's own stream; pass
+ * NULL to return to the context's stream. */
+int hem_set_stream(hem_ctx* ctx, void* stream);
+
+/* Options (all optional):
+ *   "timing"      1 -> record CUDA events around every stage (hem_step_stats ms fields)
+ *   "keep_pairs"  1 -> retain each step's (parent, child, wL) lists for hem_step_pairs
+ *   "cell_scale"  grid cell = cell_scale * mean parent radius (default 1.0)
+ *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
+ *                 (the reference consumes one draw per level-0 component first,
+ *                 src/cpp_ext/src/mixture.cpp:330, then one per pre-filter
+ *                 output, :257-259) */
+int hem_set_option(hem_ctx* ctx, const char* name, double value);
+
+/* Build `cluster_level` HEM levels from the n input splats — replaces
+ * MixtureCreator::CreateMixture (src/cpp_ext/mixture_wrapper.cpp:10-18 ->
+ * Mixture::initMixture src/cpp_ext/src/mixture.cpp:287-333 and
+ * Mixture::createClusterLevel :66-285, once per level).
+ *   xyz      [n*3]  means
+ *   color    [n*3]  raw SH-DC colour
+ *   opacity  [n]    raw opacity
+ *   cov6     [n*6]  packed covariance 00,01,02,11,12,22 (src/utils/general_utils.py:20-29)
+ *   sh       [n*sh_floats] SH rest coefficients (may be NULL iff sh_floats == 0)
+ *   weight   [n] or NULL (=> 1.0f, mixture.cpp:315); non-NULL for teacher-forced per-level parity
+ *   level0_parent_mask [n] or NULL (=> Philox flags with counters 0..n-1)
+ * Arguments 9-13 are CreateMixture's clusterLevel, hemReduction, distanceDelta,
+ * colorDelta, decayRate with unchanged meaning.  Levels 1..cluster_level are
+ * retained in the context (level 0 = the input, also retained) until the next
+ * build or hem_destroy.  Synchronous: results are complete on return. */
+int hem_build_pyramid(hem_ctx* ctx,
+                      const float* xyz, const float* color, const float* opacity,
+                      const float* cov6, const float* sh, const float* weight,
+                      int64_t n, int32_t sh_floats,
+                      uint32_t cluster_level, float hem_reduction, float distance_delta,
+                      float color_delta, float decay_rate,
+                      const uint8_t* level0_parent_mask);
+
+/* Number of levels held (cluster_level + 1, level 0 = input) and size of one —
+ * replaces len(result) / len(level.pointSet) on the reference's return value. */
+int     hem_num_levels(const hem_ctx* ctx);
+int64_t hem_level_size(const hem_ctx* ctx, int level);
+
+/* Copy one level out in the reference's array layout — replaces
+ * MixtureLevel::CreatePythonLists (src/cpp_ext/src/mixturelevel.cpp:30-70) and
+ * Mixture::GetResult (src/cpp_ext/src/mixture.cpp:335-370).  Any pointer may be
+ * NULL to skip that attribute.  `weight` and `is_parent` are not exported by
+ * the reference API; they exist for parity checks. */
+int hem_level_copy(hem_ctx* ctx, int level,
+                   float* xyz, float* color, float* opacity, float* cov6, float* sh,
+                   float* weight, uint8_t* is_parent);
+
+/* Per-step statistics of clustering step `step` (input = level `step`).
+ * out[0..15]:
+ *   0 n_in  1 n_parents  2 n_pairs  3 n_orphans  4 n_dropped  5 n_out
+ *   6 grid_cells  7 cell_size  8 max_radius
+ *   9 ms_total  10 ms_prep  11 ms_grid  12 ms_gate  13 ms_sumlw  14 ms_moments  15 ms_compact
+ * ms_* are CUDA-event times on the context's stream and are 0 unless the
+ * "timing" option is set. */
+#define HEM_STEP_STATS_LEN 16
+int hem_step_stats(const hem_ctx* ctx, int step, double* out);
+
+/* White-box access for parity tests (requires option "keep_pairs"): the
+ * accepted (parent, child) pairs of clustering step `step`, parent-major in
+ * ascending parent index; `off` has n_parents+1 entries.  Children inside a
+ * parent are in this implementation's accumulation order (not sorted).  Any
+ * pointer may be NULL.  The reference keeps these as locals of
+ * createClusterLevel (src/cpp_ext/src/mixture.cpp:103,140) and never exports
+ * them. */
+int hem_step_pairs(hem_ctx* ctx, int step, uint32_t* parent_idx, int64_t* off,
+                   uint32_t* child, float* wl, float* sumlw, float* radius);
+
+/* ---- multi-GPU (one process per GPU; spatial-slab ownership of parents) ---- */
+
+/* Size of an NCCL unique id and a getter for rank 0 to create one (the caller
+ * broadcasts the bytes to the other ranks by any means, e.g. torch.distributed). */
+#define HEM_NCCL_ID_BYTES 128
+int hem_nccl_unique_id(uint8_t* id_out);
+
+/* Join a communicator of `world` ranks.  After this, hem_build_pyramid must be
+ * called collectively with identical arguments on every rank; each rank
+ * processes the parents of its slab and every level's reduced set is
+ * all-gathered, so every rank ends with the complete pyramid. */
+int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world);
+
+/* Library/ABI version (major*1000 + minor). */
+int hem_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEM_B200_H */
