@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — HEM pyramid throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one full pass of the hot path — build the 5-level HEM pyramid of one
+synthetic 1M-Gaussian SH-degree-3 splat cloud (BASELINE.json configs[1]) — with
+the inputs already resident in HBM.  `value` = (sum over levels of the level's
+input Gaussians) * steps * ranks / timed seconds, i.e. pyramid throughput
+SUM(N_l)/SUM(t_l) in Gaussians/s.  `e2e` is the same metric through the public
+API with pinned HOST buffers: H2D of the cloud and D2H of every returned level
+inside the timed region.  `--impl reference` times the reference's own CPU
+implementation (oracle/_ref, the unmodified cpp_ext; else the C port) on the
+box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "HEM Gaussians reduced/sec per level (pyramid SUM N_l / SUM t_l)"
+UNIT = "Gaussians/s"
+ROW_BYTES = 236            # 59 floats per splat at SH degree 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--levels", type=int, default=5)
+    ap.add_argument("--density", type=float, default=5000.0)
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": f"HEM {a.levels}-level pyramid, synthetic {a.n}-Gaussian SH-deg-3 splat, density "
+                        f"{a.density:g}/unit^3, geometric+colour distance (BASELINE configs[1])",
+            "n": a.n, "levels": a.levels, "density": a.density, "sh_degree": 3,
+            "params": {"hem_reduction": 3.0, "distance_delta": 3.0, "color_delta": 2.5, "decay_rate": 1.0},
+            "parallelism": "single GPU" if world == 1 else f"{world} ranks, one independent cloud per rank (replicas)",
+            "l2": "no flush: the level-0 working set (geometry 64 MB + SH 192 MB + sort/pair buffers) exceeds the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_run(cloud, levels, nthreads):
+    """One run of the reference CPU implementation; returns (sum N_l, sum t_l seconds, kind, sizes)."""
+    from oracle import refhem
+    if refhem.available():
+        r = refhem.run(*cloud.arrays(), levels=levels, seed=7, nthreads=nthreads)
+        kind = "reference"
+    else:
+        from oracle import porthem
+        r = porthem.run(*cloud.arrays(), levels=levels, seed=7, nthreads=nthreads)
+        kind = "port"
+    sizes = [r.size(l) for l in range(levels + 1)]
+    secs = sum(r.seconds(l) for l in range(levels))
+    tot = sum(sizes[:levels])
+    r.close()
+    return tot, secs, kind, sizes
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    from gaussiansplattingregistration_b200.synth import synth
+    cores = os.cpu_count() or 1
+    n_s = a.cpu_sample if (a.steps + a.warmup) <= 20 else max(50_000, a.cpu_sample // 2)
+    cloud = synth(n_s, seed=1, density=a.density)
+    kind = "reference"
+    for _ in range(a.warmup):
+        cpu_reference_run(cloud, a.levels, cores)
+    tot = secs = 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        t, s, kind, sizes = cpu_reference_run(cloud, a.levels, cores)
+        tot += t
+        secs += s
+    wall = time.perf_counter() - t0
+    value = tot / secs
+    sample = f"{n_s}-Gaussian sample of the workload (same density/params/levels), per-level createClusterLevel time"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": wall, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------- own arm
+def run_b200_arm(a, rank, local_rank, world):
+    import torch
+    from gaussiansplattingregistration_b200.hem import HemContext
+    from gaussiansplattingregistration_b200.synth import synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cloud = synth(a.n, seed=1 + rank, density=a.density)
+    dev = [torch.from_numpy(x).cuda() for x in cloud.arrays()]
+    ctx = HemContext(local_rank, seed=7)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_option("timing", 1)
+
+    for _ in range(max(a.warmup, 3)):
+        ctx.build(*dev, cluster_level=a.levels)
+    stats = [ctx.step_stats(l) for l in range(a.levels)]
+    sum_n = sum(s["n_in"] for s in stats)
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.info("launches")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gate_ms = gate_bytes = mom_ms = mom_bytes = 0.0
+    lvl_ms = [0.0] * a.levels
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        ctx.build(*dev, cluster_level=a.levels)
+        for l in range(a.levels):            # host-side bookkeeping of the event times the library recorded
+            s = ctx.step_stats(l)
+            lvl_ms[l] += s["ms_total"]
+            gate_ms += s["ms_k_gate"]
+            mom_ms += s["ms_k_moments"]
+            # algorithmic bytes, SURVEY.md §8(d): S3 = 60N + 60Np + 12P + 4N ; S4 = 12P + 236 N_claimed + 236 Np
+            gate_bytes += 60 * s["n_in"] + 60 * s["n_parents"] + 12 * s["n_pairs"] + 4 * s["n_in"]
+            mom_bytes += 12 * s["n_pairs"] + ROW_BYTES * (s["n_in"] - s["n_orphans"]) + ROW_BYTES * s["n_parents"]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.info("launches") - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = sum_n * a.steps * world / (ms / 1e3)
+
+    # ---- end to end through the public API with pinned host buffers ----------------------------
+    if a.skip_e2e:
+        if rank == 0:
+            print(json.dumps({'profile_only': True, 'value': value, 'ms_per_step': ms / a.steps}))
+        return
+    host_in = [torch.from_numpy(x).pin_memory() for x in cloud.arrays()]
+    host_np = [h.numpy() for h in host_in]
+    sizes = [ctx.level_size(l) for l in range(a.levels + 1)]
+    cap = max(sizes[1:]) if a.levels else 0
+    F = cloud.sh_floats
+    outb = [torch.empty((cap, 3), dtype=torch.float32).pin_memory(), torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
+            torch.empty(cap, dtype=torch.float32).pin_memory(), torch.empty((cap, 6), dtype=torch.float32).pin_memory(),
+            torch.empty((cap, F), dtype=torch.float32).pin_memory()]
+    outn = [o.numpy() for o in outb]
+
+    def e2e_step():
+        ctx.build(*host_np, cluster_level=a.levels)
+        for l in range(1, a.levels + 1):
+            ctx.level_into(l, *outn)
+
+    for _ in range(2):
+        e2e_step()
+    k_e2e = max(3, min(a.steps, 5))
+    h0, d0 = ctx.info("bytes_h2d"), ctx.info("bytes_d2h")
+    barrier()
+    e0.record()
+    for _ in range(k_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = sum_n * k_e2e * world / (e2e_ms / 1e3)
+    h2d = (ctx.info("bytes_h2d") - h0) / k_e2e
+    d2h = (ctx.info("bytes_d2h") - d0) / k_e2e
+
+    if rank != 0:
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    gate_gbs = gate_bytes / (gate_ms * 1e-3) / 1e9 if gate_ms > 0 else 0.0
+    mom_gbs = mom_bytes / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else 0.0
+    lvl = [{"level": l, "n_in": stats[l]["n_in"], "n_parents": stats[l]["n_parents"], "n_pairs": stats[l]["n_pairs"],
+            "n_out": stats[l]["n_out"], "ms": lvl_ms[l] / a.steps,
+            "gaussians_per_s": stats[l]["n_in"] / (lvl_ms[l] / a.steps * 1e-3) if lvl_ms[l] > 0 else None}
+           for l in range(a.levels)]
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_ms / k_e2e, "steps": k_e2e},
+           "gpu_launches": int(launches),
+           "roofline": {"kernel": "hem::k_gate (gates + likelihood)", "bound": "hbm", "achieved": gate_gbs, "peak": peak,
+                        "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None, "peak_source": peak_src,
+                        "bytes_per_launch": gate_bytes / (a.steps * a.levels), "ms_per_launch": gate_ms / (a.steps * a.levels),
+                        "note": "ALU/L2-bound by construction (SURVEY.md §8d): ~100 in-radius candidates per parent against 60 B of compulsory traffic per child"},
+           "kernels": {"k_gate": {"gbs": gate_gbs, "frac": gate_gbs / peak, "ms_per_step": gate_ms / a.steps},
+                       "k_moments": {"gbs": mom_gbs, "frac": mom_gbs / peak, "ms_per_step": mom_ms / a.steps}},
+           "levels": lvl}
+    if world == 1 and not a.no_cpu_baseline:
+        from gaussiansplattingregistration_b200.synth import synth as _s
+        cores = os.cpu_count() or 1
+        sample_cloud = _s(a.cpu_sample, seed=1, density=a.density)
+        tot, secs, kind, _ = cpu_reference_run(sample_cloud, a.levels, cores)
+        out["cpu_baseline"] = {"value": tot / secs, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"{a.cpu_sample}-Gaussian sample of the workload (same density/params/levels), "
+                                         f"one run, per-level createClusterLevel time {secs:.2f} s"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+    run_b200_arm(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

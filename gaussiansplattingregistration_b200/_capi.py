@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhem_b200.so")
 
-STEP_STATS_LEN = 16
+STEP_STATS_LEN = 18
 NCCL_ID_BYTES = 128
 
 _f = C.POINTER(C.c_float)
@@ -37,6 +37,7 @@ SIGNATURES = {
     "hem_level_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "hem_step_stats": (C.c_int, [C.c_void_p, C.c_int, _d]),
+    "hem_get_info": (C.c_int, [C.c_void_p, C.c_char_p, _d]),
     "hem_step_pairs": (C.c_int, [C.c_void_p, C.c_int, _u32, _i64, _u32, _f, _f, _f]),
     "hem_nccl_unique_id": (C.c_int, [_u8]),
     "hem_comm_init": (C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int]),

@@ -39,7 +39,7 @@ struct Level {
 struct StepStats {
     int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0;
     double cell_size = 0, max_radius = 0;
-    double ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact
+    double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
 };
 
 struct StepPairs {
@@ -48,7 +48,7 @@ struct StepPairs {
     std::vector<float> wl, sumlw, radius;
 };
 
-enum { EV_BEGIN = 0, EV_PREP, EV_GRID, EV_GATE, EV_SUMLW, EV_MOM, EV_END, EV_COUNT };
+enum { EV_BEGIN = 0, EV_PREP, EV_GRID, EV_GATE, EV_SUMLW, EV_MOM, EV_END, EV_GK0, EV_GK1, EV_MK0, EV_MK1, EV_COUNT };
 
 } // namespace
 
@@ -63,6 +63,7 @@ struct hem_ctx {
     uint64_t rng_base = 0;
     int F = 0, Fp = 0;
     int sm_count = 148;
+    uint64_t n_launches = 0, bytes_h2d = 0, bytes_d2h = 0;
 
     std::vector<Level> levels;
     std::vector<StepStats> stats;
@@ -136,6 +137,7 @@ int to_device(hem_ctx* ctx, const void* src, size_t bytes, DevBuf& stage, const 
     if (is_device_ptr(src)) { *out = src; return HEM_OK; }
     CKR(ensure(ctx, stage, bytes));
     CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytes_h2d += bytes;
     *out = stage.p;
     return HEM_OK;
 }
@@ -198,7 +200,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     }
     k_prep<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, distance_delta, ctx->radius.as<float>(),
                                                 ctx->pflag.as<uint32_t>(), ctx->prep.as<PrepStats>());
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
     }));
@@ -273,7 +275,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->psorted, np * 4));
         CKR(ensure(ctx, ctx->nsel, 8));
         k_cellkey<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, g, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
         const int kbits = bits_for(ncell - 1);
         CKR(cub_call(ctx, [&](void* t, size_t& b) {
             return cub::DeviceRadixSort::SortPairs(t, b, ctx->key.as<uint32_t>(), ctx->key2.as<uint32_t>(),
@@ -283,7 +285,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                              ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                              ctx->sp2.as<float4>(), ctx->sp3.as<float4>(),
                                                              ctx->sflag.as<uint8_t>(), ctx->cell_start.as<uint32_t>());
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
         CKR(cub_call(ctx, [&](void* t, size_t& b) {
             return cub::DeviceSelect::Flagged(t, b, thrust::counting_iterator<uint32_t>(0), ctx->sflag.as<uint8_t>(),
                                               ctx->psorted.as<uint32_t>(), ctx->nsel.as<uint32_t>(), (int)n, st);
@@ -312,8 +314,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
             A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
             A.counters = ctx->counters.as<unsigned long long>();
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
             k_gate<<<blocks_for(np, GATE_WARPS), GATE_WARPS * 32, 0, st>>>(A);
             CK(cudaGetLastError());
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK1], st));
+            ctx->n_launches++;
             CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                              // sync B
             if (ctx->h_counters[C_POOL] <= pool_cap && ctx->h_counters[C_CHUNK] <= chunk_cap) break;
@@ -334,7 +339,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
                 ctx->chunks.as<uint4>(), nchunks, ctx->pool.as<uint2>(), ctx->pair_off.as<uint32_t>(),
                 ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
-            CK(cudaGetLastError());
+            CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
 
@@ -349,7 +354,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             }));
             k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P,
                                                           ctx->sumlw.as<float>());
-            CK(cudaGetLastError());
+            CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
 
@@ -360,8 +365,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         M.csr_child = ctx->csr_child.as<uint32_t>(); M.csr_wl = ctx->csr_wl.as<float>(); M.sumlw = ctx->sumlw.as<float>();
         M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>(); M.valid = ctx->valid.as<uint8_t>();
         M.seed = ctx->seed; M.rng_base = rng_base; M.pp = pp; M.counters = ctx->counters.as<unsigned long long>();
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         k_moments<<<blocks_for(np, MOM_WARPS), MOM_WARPS * 32, 0, st>>>(M);
         CK(cudaGetLastError());
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK1], st));
+        ctx->n_launches++;
     } else if (ctx->timing) {
         CK(cudaEventRecord(ctx->ev[EV_GRID], st));
         CK(cudaEventRecord(ctx->ev[EV_GATE], st));
@@ -373,7 +381,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CKR(ensure(ctx, ctx->oflag, n * 4));
     CKR(ensure(ctx, ctx->orank, n * 4));
     k_orphan_flag<<<blocks_for(n, 256), 256, 0, st>>>(ctx->sumlw.as<float>(), n, ctx->oflag.as<uint32_t>());
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(), (int)n, st);
     }));
@@ -381,7 +389,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                    (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>(),
                                                    ctx->valid.as<uint8_t>(), ctx->seed, rng_base, pp,
                                                    ctx->counters.as<unsigned long long>());
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); ctx->n_launches++;
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->orank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ctx->h_counters[9], ctx->oflag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -402,14 +410,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->tmp_geo, (size_t)npre * 64));
         CKR(ensure(ctx, ctx->tmp_sh, (size_t)npre * std::max(Fp, 1) * 4));
         k_valid_flag<<<blocks_for(npre, 256), 256, 0, st>>>(ctx->valid.as<uint8_t>(), npre, ctx->vflag.as<uint32_t>());
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
         CKR(cub_call(ctx, [&](void* t, size_t& b) {
             return cub::DeviceScan::ExclusiveSum(t, b, ctx->vflag.as<uint32_t>(), ctx->vpos.as<uint32_t>(), (int)npre, st);
         }));
         k_compact_rows<<<blocks_for(npre * 32, 256), 256, 0, st>>>(out.geo.as<float4>(), out.sh.as<float>(), Fp, npre,
                                                                     ctx->valid.as<uint8_t>(), ctx->vpos.as<uint32_t>(),
                                                                     ctx->tmp_geo.as<float4>(), ctx->tmp_sh.as<float>());
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
         const int64_t nout = npre - ninvalid;
         CK(cudaMemcpyAsync(out.geo.p, ctx->tmp_geo.p, (size_t)nout * 64, cudaMemcpyDeviceToDevice, st));
         if (Fp > 0) CK(cudaMemcpyAsync(out.sh.p, ctx->tmp_sh.p, (size_t)nout * Fp * 4, cudaMemcpyDeviceToDevice, st));
@@ -427,6 +435,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         cudaEventElapsedTime(&ms, ctx->ev[EV_GATE], ctx->ev[EV_SUMLW]); S.ms[4] = ms;
         cudaEventElapsedTime(&ms, ctx->ev[EV_SUMLW], ctx->ev[EV_MOM]); S.ms[5] = ms;
         cudaEventElapsedTime(&ms, ctx->ev[EV_MOM], ctx->ev[EV_END]); S.ms[6] = ms;
+        if (have_pairs) {
+            cudaEventElapsedTime(&ms, ctx->ev[EV_GK0], ctx->ev[EV_GK1]); S.ms[7] = ms;
+            cudaEventElapsedTime(&ms, ctx->ev[EV_MK0], ctx->ev[EV_MK1]); S.ms[8] = ms;
+        }
     }
 
     if (ctx->keep_pairs) {
@@ -579,10 +591,10 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
         k_import<<<blocks_for(n, 256), 256, 0, st>>>((const float*)dx, (const float*)dc, (const float*)dop,
                                                       (const float*)dcv, (const float*)dw, (const uint8_t*)dm,
                                                       L0.geo.as<float4>(), n, ctx->seed, 1.0f / hem_reduction);
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
         if (Fp > 0) {
             k_pad_sh<<<blocks_for(n * Fp, 256), 256, 0, st>>>((const float*)dsh, L0.sh.as<float>(), n, sh_floats, Fp);
-            CK(cudaGetLastError());
+            CK(cudaGetLastError()); ctx->n_launches++;
         }
     }
     uint64_t base = ctx->rng_base_set ? ctx->rng_base : (uint64_t)n;
@@ -635,10 +647,10 @@ int hem_level_copy(hem_ctx* ctx, int level, float* xyz, float* color, float* opa
     CKR(from_device(ctx, is_parent, (size_t)n, ctx->out_g, &df, &sf));
     k_export<<<blocks_for(n, 256), 256, 0, st>>>(L.geo.as<float4>(), n, (float*)dx, (float*)dc, (float*)dop, (float*)dcv,
                                                   (float*)dw, (uint8_t*)df);
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); ctx->n_launches++;
     if (dsh) {
         k_unpad_sh<<<blocks_for(n * F, 256), 256, 0, st>>>(L.sh.as<float>(), (float*)dsh, n, F, Fp);
-        CK(cudaGetLastError());
+        CK(cudaGetLastError()); ctx->n_launches++;
     }
     if (sx) CK(cudaMemcpyAsync(xyz, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     if (sc) CK(cudaMemcpyAsync(color, dc, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
@@ -648,6 +660,8 @@ int hem_level_copy(hem_ctx* ctx, int level, float* xyz, float* color, float* opa
     if (sw) CK(cudaMemcpyAsync(weight, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (sf) CK(cudaMemcpyAsync(is_parent, df, (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ctx->bytes_d2h += (sx ? (size_t)n * 12 : 0) + (sc ? (size_t)n * 12 : 0) + (sop ? (size_t)n * 4 : 0) +
+                      (scv ? (size_t)n * 24 : 0) + (ssh ? (size_t)n * F * 4 : 0) + (sw ? (size_t)n * 4 : 0) + (sf ? (size_t)n : 0);
     return HEM_OK;
 }
 
@@ -658,7 +672,7 @@ int hem_step_stats(const hem_ctx* ctx, int step, double* out)
     out[0] = (double)S.n_in; out[1] = (double)S.n_parents; out[2] = (double)S.n_pairs; out[3] = (double)S.n_orphans;
     out[4] = (double)S.n_dropped; out[5] = (double)S.n_out; out[6] = (double)S.grid_cells; out[7] = S.cell_size;
     out[8] = S.max_radius;
-    for (int i = 0; i < 7; ++i) out[9 + i] = S.ms[i];
+    for (int i = 0; i < 9; ++i) out[9 + i] = S.ms[i];
     return HEM_OK;
 }
 
@@ -674,6 +688,20 @@ int hem_step_pairs(hem_ctx* ctx, int step, uint32_t* parent_idx, int64_t* off, u
     if (wl) memcpy(wl, K.wl.data(), K.wl.size() * 4);
     if (sumlw) memcpy(sumlw, K.sumlw.data(), K.sumlw.size() * 4);
     if (radius) memcpy(radius, K.radius.data(), K.radius.size() * 4);
+    return HEM_OK;
+}
+
+int hem_get_info(const hem_ctx* ctx, const char* name, double* out)
+{
+    if (!ctx || !name || !out) return HEM_ERR_INVALID;
+    std::string k(name);
+    if (k == "launches") *out = (double)ctx->n_launches;
+    else if (k == "bytes_h2d") *out = (double)ctx->bytes_h2d;
+    else if (k == "bytes_d2h") *out = (double)ctx->bytes_d2h;
+    else if (k == "sm_count") *out = (double)ctx->sm_count;
+    else if (k == "world") *out = (double)ctx->world;
+    else if (k == "rank") *out = (double)ctx->rank;
+    else return HEM_ERR_INVALID;
     return HEM_OK;
 }
 

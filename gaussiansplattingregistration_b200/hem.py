@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi
 
 STAT_NAMES = ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out", "grid_cells", "cell_size",
-              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact")
+              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments")
 
 
 @dataclass
@@ -139,6 +139,25 @@ class HemContext:
             C.c_void_p(out["sh"].ctypes.data) if F else None, w, f))
         return out
 
+    def level_into(self, level: int, xyz=None, colors=None, opacity=None, cov6=None, sh=None,
+                   weight=None, is_parent=None) -> int:
+        """Copy one level into caller-owned buffers (numpy arrays, e.g. views of pinned
+        torch tensors, or torch CUDA tensors); returns the level size.  Buffers must be
+        contiguous float32 (uint8 for is_parent) with room for level_size rows."""
+        ptrs = []
+        keep = []
+        for a in (xyz, colors, opacity, cov6, sh if self.sh_floats else None, weight, is_parent):
+            if a is None:
+                ptrs.append(None)
+            elif _is_torch(a):
+                ptrs.append(C.c_void_p(a.data_ptr()))
+            else:
+                assert a.flags["C_CONTIGUOUS"]
+                ptrs.append(C.c_void_p(a.ctypes.data))
+            keep.append(a)
+        self._check(self._lib.hem_level_copy(self._h, level, *ptrs))
+        return self.level_size(level)
+
     def level_torch(self, level: int, with_internal: bool = False) -> dict:
         """One level as torch CUDA tensors (device-to-device, no host staging)."""
         import torch
@@ -167,6 +186,11 @@ class HemContext:
         for k in STAT_NAMES[:7]:
             d[k] = int(d[k])
         return d
+
+    def info(self, name: str) -> float:
+        out = C.c_double(0)
+        self._check(self._lib.hem_get_info(self._h, name.encode(), C.byref(out)))
+        return float(out.value)
 
     def step_pairs(self, step: int) -> dict:
         """White-box child lists of a step (needs option keep_pairs=1 before build)."""

@@ -107,10 +107,16 @@ int hem_level_copy(hem_ctx* ctx, int level,
  *   0 n_in  1 n_parents  2 n_pairs  3 n_orphans  4 n_dropped  5 n_out
  *   6 grid_cells  7 cell_size  8 max_radius
  *   9 ms_total  10 ms_prep  11 ms_grid  12 ms_gate  13 ms_sumlw  14 ms_moments  15 ms_compact
+ *   16 ms_k_gate (the gate kernel alone)  17 ms_k_moments (the moment kernel alone)
  * ms_* are CUDA-event times on the context's stream and are 0 unless the
  * "timing" option is set. */
-#define HEM_STEP_STATS_LEN 16
+#define HEM_STEP_STATS_LEN 18
 int hem_step_stats(const hem_ctx* ctx, int step, double* out);
+
+/* Cumulative counters of the context: "launches" (kernels of this library
+ * launched so far), "bytes_h2d" / "bytes_d2h" (bytes staged across PCIe for
+ * host-pointer arguments), "sm_count", "rank", "world". */
+int hem_get_info(const hem_ctx* ctx, const char* name, double* out);
 
 /* White-box access for parity tests (requires option "keep_pairs"): the
  * accepted (parent, child) pairs of clustering step `step`, parent-major in

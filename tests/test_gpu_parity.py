@@ -1,0 +1,225 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through
+the C ABI of libhem_b200.so; the oracle (oracle/hem_oracle.c, and the compiled
+reference oracle/_ref where it travelled) is only the checker."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+from _parity import TOL, assert_children_equal, assert_level_close, group_relerr, inputs_of, sort_children
+from gaussiansplattingregistration_b200.synth import synth
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("xyz", "colors", "opacity", "cov6", "sh", "weight", "is_parent")
+
+
+def gpu_step_children(ctx, step):
+    p = ctx.step_pairs(step)
+    return p
+
+
+def compare_free_running(ctx, ref_levels, ref_children, nlevels, what):
+    """counts/order/flags exact, values within tolerance, child sets exact."""
+    for l in range(nlevels + 1):
+        assert_level_close(ctx.level(l, with_internal=True), ref_levels(l), what=f"{what} level {l}")
+    for l in range(nlevels):
+        g = ctx.step_pairs(l)
+        pidx, off, child = ref_children(l)
+        assert_children_equal(g["parent_idx"], g["off"], g["child"], pidx, off, child, what=f"{what} step {l}")
+
+
+@pytest.mark.parametrize("n,density,levels", [(3000, 20000.0, 3), (20000, 5000.0, 4), (50000, 1000.0, 3),
+                                              (100000, 5000.0, 2)])
+def test_gpu_vs_oracle_free_running(hemctx, port, n, density, levels):
+    c = synth(n, seed=31, density=density)
+    hemctx.build(*c.arrays(), cluster_level=levels)
+    r = port.run(*c.arrays(), levels=levels, seed=7)
+
+    def children(l):
+        ch = r.children(l)
+        return ch["parent_idx"], ch["off"], ch["child"]
+    compare_free_running(hemctx, r.level, children, levels, f"n={n}")
+    # likelihood weights and per-child normalisers (tolerance class: expf)
+    g, o = hemctx.step_pairs(0), r.children(0)
+    gc, gwl = sort_children(g["off"], g["child"], g["wl"])
+    assert group_relerr(gwl, o["wl"]) < 1e-5
+    assert group_relerr(g["sumlw"], o["sumlw"]) < 1e-5
+    assert np.array_equal(g["sumlw"] == 0, o["sumlw"] == 0)            # orphan set, bit-exact
+    assert np.array_equal(g["radius"], o["radius"])                     # query radii at level 0, bit-exact
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gpu_teacher_forced_on_reference_golden(name):
+    """SURVEY.md §7 mode A: the GPU runs ONE step on the REFERENCE's own level-l
+    rows, weights and flags; masks, child sets, orphan sets, counts and order must
+    be bit-exact with the recorded reference, values within 1e-4."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    g = load_golden(name)
+    red, dd, cd, decay = (float(v) for v in g["params"])
+    base = int(g["n"])
+    with HemContext(0, seed=int(g["seed"])) as ctx:
+        ctx.set_option("keep_pairs", 1)
+        for l in range(int(g["levels"])):
+            lvl = {k: g[f"L{l}_{k}"] for k in KEYS}
+            ctx.set_option("rng_base", base)
+            ctx.build(*inputs_of(lvl), cluster_level=1, hem_reduction=red, distance_delta=dd, color_delta=cd,
+                      decay_rate=decay, weight=lvl["weight"], parent_mask=lvl["is_parent"])
+            p = ctx.step_pairs(0)
+            assert_children_equal(p["parent_idx"], p["off"], p["child"], g[f"S{l}_parent_idx"], g[f"S{l}_off"],
+                                  g[f"S{l}_child"], what=f"{name} step {l}")
+            want = {k: g[f"L{l+1}_{k}"] for k in KEYS}
+            assert_level_close(ctx.level(1, with_internal=True), want, what=f"{name} level {l+1}")
+            st = ctx.step_stats(0)
+            base += st["n_parents"] + st["n_orphans"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gpu_free_running_on_reference_golden(hemctx, name):
+    g = load_golden(name)
+    red, dd, cd, decay = (float(v) for v in g["params"])
+    L = int(g["levels"])
+    from gaussiansplattingregistration_b200.hem import HemContext
+    ctx = HemContext(0, seed=int(g["seed"]))
+    ctx.set_option("keep_pairs", 1)
+    ctx.build(g["xyz"], g["colors"], g["opacity"], g["cov6"], g["sh"], cluster_level=L, hem_reduction=red,
+              distance_delta=dd, color_delta=cd, decay_rate=decay)
+    compare_free_running(ctx, lambda l: {k: g[f"L{l}_{k}"] for k in KEYS},
+                         lambda l: (g[f"S{l}_parent_idx"], g[f"S{l}_off"], g[f"S{l}_child"]), L, name)
+    ctx.close()
+
+
+def test_gpu_vs_compiled_reference_live(hemctx):
+    """Against the UNMODIFIED reference cpp_ext itself (oracle/_ref travels to the box prebuilt)."""
+    from oracle import refhem
+    if not refhem.available():
+        pytest.skip("oracle/_ref/libhemref.so not present on this box")
+    c = synth(30000, seed=41, density=5000.0)
+    ref = refhem.run(*c.arrays(), levels=3, seed=7)
+    hemctx.build(*c.arrays(), cluster_level=3)
+    compare_free_running(hemctx, ref.level, ref.children, 3, "vs reference")
+    # teacher-forced per level on the reference's own intermediate levels
+    base = c.n
+    for l in range(3):
+        lvl = ref.level(l)
+        hemctx.set_option("rng_base", base)
+        hemctx.build(*inputs_of(lvl), cluster_level=1, weight=lvl["weight"], parent_mask=lvl["is_parent"])
+        p = hemctx.step_pairs(0)
+        pidx, off, child = ref.children(l)
+        assert_children_equal(p["parent_idx"], p["off"], p["child"], pidx, off, child, what=f"teacher-forced step {l}")
+        assert np.array_equal(p["radius"], ref.radii(l)[pidx]), "query radii not bit-exact"
+        assert_level_close(hemctx.level(1, with_internal=True), ref.level(l + 1), what=f"teacher-forced level {l+1}")
+        st = hemctx.step_stats(0)
+        base += st["n_parents"] + st["n_orphans"]
+    hemctx.set_option("rng_base", -1)
+
+
+def test_gpu_edge_cases(hemctx, port):
+    c = synth(700, seed=4, density=5000.0, sh_degree=2)
+    # cluster level 0
+    assert hemctx.build(*c.arrays(), cluster_level=0) == 1 and hemctx.level_size(0) == 700
+    # no parent selected -> the level is an ordered copy
+    hemctx.build(*c.arrays(), cluster_level=2, parent_mask=np.zeros(700, np.uint8))
+    a, b = hemctx.level(0, True), hemctx.level(1, True)
+    for k in ("xyz", "colors", "opacity", "cov6", "sh", "weight"):
+        assert np.array_equal(a[k], b[k])
+    r = port.run(*c.arrays(), levels=2, seed=7, mask=np.zeros(700, np.uint8), rng_base=700)
+    for l in range(3):
+        assert_level_close(hemctx.level(l, True), r.level(l), what=f"no-parent level {l}")
+    # every component a parent -> each keeps only itself
+    hemctx.build(*c.arrays(), cluster_level=1, parent_mask=np.ones(700, np.uint8))
+    p = hemctx.step_pairs(0)
+    assert np.array_equal(p["child"], np.arange(700, dtype=np.uint32))
+    # empty input
+    e = synth(0, seed=0)
+    assert hemctx.build(*e.arrays(), cluster_level=2) == 3
+    assert [hemctx.level_size(l) for l in range(3)] == [0, 0, 0]
+    assert hemctx.level(1)["xyz"].shape == (0, 3)
+    # no SH at all (F = 0) and a single splat
+    one = synth(1, seed=9, sh_degree=0)
+    hemctx.build(*one.arrays(), cluster_level=1, parent_mask=np.ones(1, np.uint8))
+    assert hemctx.level_size(1) == 1
+    assert_level_close(hemctx.level(1), {k: v for k, v in zip(("xyz", "colors", "opacity", "cov6", "sh"), one.arrays())}, tol=1e-6)
+    # bad arguments come back as errors, not crashes
+    from gaussiansplattingregistration_b200._capi import HemError
+    with pytest.raises(HemError):
+        hemctx.build(*c.arrays(), cluster_level=1, hem_reduction=0.0)
+    with pytest.raises(HemError):
+        hemctx.level_size(99)
+
+
+def test_gpu_heavy_tail_and_large_radius(hemctx, port):
+    """Unclipped log-normal scales: a few parents cover a large part of the cloud
+    (the reference's worst case)."""
+    c = synth(20000, seed=17, density=20000.0, clip_sigma=None, scale_sigma_ln=0.8)
+    hemctx.build(*c.arrays(), cluster_level=2)
+    r = port.run(*c.arrays(), levels=2, seed=7)
+
+    def children(l):
+        ch = r.children(l)
+        return ch["parent_idx"], ch["off"], ch["child"]
+    compare_free_running(hemctx, r.level, children, 2, "heavy tail")
+
+
+def test_gpu_determinism_and_pointer_kinds(hemctx):
+    """Two runs are bit-identical; device-pointer inputs/outputs equal host-pointer ones."""
+    import torch
+    c = synth(60000, seed=23, density=5000.0)
+    hemctx.build(*c.arrays(), cluster_level=3)
+    a = [hemctx.level(l, True) for l in range(4)]
+    dev = [torch.from_numpy(x).cuda() for x in c.arrays()]
+    hemctx.build(*dev, cluster_level=3)
+    for l in range(4):
+        b = hemctx.level(l, True)
+        t = hemctx.level_torch(l, True)
+        for k in KEYS:
+            assert np.array_equal(a[l][k], b[k]), f"run-to-run difference at level {l} {k}"
+            assert np.array_equal(t[k].cpu().numpy(), b[k]), f"device/host copy difference at level {l} {k}"
+
+
+def test_gpu_full_size_properties(hemctx):
+    """BASELINE config 2 size (1M splats, 5 levels): size-independent properties
+    instead of an oracle run — mass conservation, weights >= 1, strictly shrinking
+    levels, parents-then-orphans order with bit-copied orphans, flag rate, PD output."""
+    n, L = 1_000_000, 5
+    c = synth(n, seed=1, density=5000.0)
+    hemctx.build(*c.arrays(), cluster_level=L)
+    prev = hemctx.level(0, True)
+    for l in range(L):
+        st = hemctx.step_stats(l)
+        cur = hemctx.level(l + 1, True)
+        assert st["n_dropped"] == 0
+        assert cur["xyz"].shape[0] == st["n_parents"] + st["n_orphans"] == st["n_out"] < st["n_in"]
+        assert abs(float(cur["weight"].astype(np.float64).sum()) - n) < n * 2e-5       # mass conservation
+        assert float(cur["weight"].min()) >= 1.0 - 1e-5
+        sumlw = hemctx.step_pairs(l)["sumlw"]
+        orphans = np.nonzero(sumlw == 0.0)[0]
+        assert len(orphans) == st["n_orphans"]
+        for k in ("xyz", "colors", "opacity", "cov6", "sh", "weight"):
+            assert np.array_equal(cur[k][st["n_parents"]:], prev[k][orphans]), f"orphans not bit-copied ({k})"
+        assert np.array_equal(np.nonzero(prev["is_parent"])[0], hemctx.step_pairs(l)["parent_idx"])
+        assert abs(float(cur["is_parent"].mean()) - 1 / 3) < 0.01
+        cc = cur["cov6"].astype(np.float64)
+        det = (-cc[:, 2] * cc[:, 2] * cc[:, 3] + 2 * cc[:, 1] * cc[:, 2] * cc[:, 4] - cc[:, 0] * cc[:, 4] * cc[:, 4]
+               - cc[:, 1] * cc[:, 1] * cc[:, 5] + cc[:, 0] * cc[:, 3] * cc[:, 5])
+        assert (det > 0).all() and np.isfinite(cur["xyz"]).all()
+        prev = cur
+
+
+def test_gpu_mixture_bind_drop_in():
+    """The reference call sequence of qt_gaussian_mixture.py:42-58,96 through the shim, lists in / lists out."""
+    from gaussiansplattingregistration_b200 import mixture_bind
+    from oracle import porthem
+    c = synth(4000, seed=51, density=5000.0)
+    mixture_bind.MixtureCreator.seed = 7
+    level = mixture_bind.MixtureLevel.CreateMixtureLevel(c.xyz.tolist(), c.colors.tolist(), c.opacity.tolist(),
+                                                        c.cov6.tolist(), c.sh.tolist())
+    models = mixture_bind.MixtureCreator.CreateMixture(3, 3.0, 3.0, 2.5, 1.0, level)
+    assert len(models) == 3
+    r = porthem.run(*c.arrays(), levels=3, seed=7)
+    for l, m in enumerate(models, start=1):
+        xyz, colors, opac, cov, feats = mixture_bind.MixtureLevel.CreatePythonLists(m)
+        assert isinstance(xyz, list) and len(xyz[0]) == 3 and len(cov[0]) == 6 and len(feats[0]) == 45
+        got = dict(xyz=np.asarray(xyz, np.float32), colors=np.asarray(colors, np.float32),
+                   opacity=np.asarray(opac, np.float32), cov6=np.asarray(cov, np.float32), sh=np.asarray(feats, np.float32))
+        want = {k: v for k, v in r.level(l).items() if k in got}
+        assert_level_close(got, want, what=f"mixture_bind level {l}")
