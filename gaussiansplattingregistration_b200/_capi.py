@@ -41,6 +41,7 @@ SIGNATURES = {
     "hem_step_pairs": (C.c_int, [C.c_void_p, C.c_int, _u32, _i64, _u32, _f, _f, _f]),
     "hem_nccl_unique_id": (C.c_int, [_u8]),
     "hem_comm_init": (C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int]),
+    "hem_slab_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, _i64, _i64]),
 }
 
 _lib = None

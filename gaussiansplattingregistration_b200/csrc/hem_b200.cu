@@ -22,6 +22,8 @@ using namespace hem;
 
 namespace {
 
+struct NcclId { char internal[128]; };
+
 thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -73,7 +75,7 @@ struct hem_ctx {
     DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
     DevBuf radius, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
-    DevBuf pair_cnt, pair_off, parent_of_rank, pool, chunks, csr_child, csr_wl, sk, sv, sumlw, oflag, orank;
+    DevBuf pair_cnt, pair_off, pair_cnt_s, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, sumlw, oflag, orank;
     DevBuf valid, vflag, vpos, cubtmp, counters, prep, nsel, tmp_geo, tmp_sh;
     unsigned long long* h_counters = nullptr;   // pinned
     PrepStats* h_prep = nullptr;                // pinned
@@ -158,6 +160,83 @@ template <class F> int cub_call(hem_ctx* ctx, F&& f)
     CKR(ensure(ctx, ctx->cubtmp, bytes));
     size_t have = ctx->cubtmp.cap;
     CK(f(ctx->cubtmp.p, have));
+    return HEM_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen) so that the single-GPU library has no NCCL
+// dependency and a process that already loaded torch's bundled NCCL shares it.
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib)
+        for (const char* nm : names) {
+            g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+    if (!g_nccl.lib) { g_nccl.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    auto sym = [&](const char* n) { return dlsym(g_nccl.lib, n); };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+        g_nccl.err = "libnccl lacks a required symbol";
+        g_nccl.lib = nullptr;
+        return false;
+    }
+    return true;
+}
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int e_ = (call);                                                                           \
+        if (e_ != 0) {                                                                             \
+            ctx->err = std::string(#call " failed: ") +                                            \
+                       (g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "nccl error");         \
+            return HEM_ERR_NCCL;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+// slab bounds: parents (in cell order) [bounds[r], bounds[r+1]) belong to rank r
+inline int64_t slab_bound(int64_t np, int r, int world) { return np * (int64_t)r / world; }
+
+// every rank owns the byte range [bounds[r]*elem, bounds[r+1]*elem) of `buf`; after the call all
+// ranks hold all ranges (grouped in-place broadcasts = an all-gather with uneven counts)
+int allgather_ranges(hem_ctx* ctx, void* buf, size_t elem, const int64_t* bounds)
+{
+    if (ctx->world <= 1) return HEM_OK;
+    NK(g_nccl.GroupStart());
+    for (int q = 0; q < ctx->world; ++q) {
+        const size_t cnt = (size_t)(bounds[q + 1] - bounds[q]) * elem;
+        if (cnt == 0) continue;
+        char* ptr = (char*)buf + (size_t)bounds[q] * elem;
+        NK(g_nccl.Broadcast(ptr, ptr, cnt, /*ncclChar*/ 0, q, ctx->nccl_comm, ctx->stream));
+    }
+    NK(g_nccl.GroupEnd());
     return HEM_OK;
 }
 
@@ -259,6 +338,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             }
             g.ox = bmin[0]; g.oy = bmin[1]; g.oz = bmin[2];
             g.inv_h = (float)(1.0 / h);
+            g.h = 1.0f / g.inv_h;
             g.gx = (int)std::min(2047.0, std::floor(ext[0] / h)) + 1;
             g.gy = (int)std::min(2047.0, std::floor(ext[1] / h)) + 1;
             g.gz = (int)std::min(2047.0, std::floor(ext[2] / h)) + 1;
@@ -293,52 +373,101 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
+        const int G = ctx->world, R = ctx->rank;
+        std::vector<int64_t> tb(G + 1);
+        for (int q = 0; q <= G; ++q) tb[q] = slab_bound(np, q, G);
+        const int64_t my_np = tb[R + 1] - tb[R];
         CKR(ensure(ctx, ctx->pair_cnt, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
-        size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n, 1 << 16));
+        CKR(ensure(ctx, ctx->pair_cnt_s, (np + 1) * 4));
+        CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
+        CKR(ensure(ctx, ctx->ptab, np * 8));
+        CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
+        k_ptab<<<blocks_for(np, 256), 256, 0, st>>>(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
+                                                     ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
+                                                     ctx->radius.as<float>(), geo, (int)np, ctx->ptab.as<uint2>(),
+                                                     ctx->pinfo.as<float4>());
+        CK(cudaGetLastError()); ctx->n_launches++;
+        size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n / G, 1 << 16));
+        unsigned long long nchunks = 0;
         for (int attempt = 0; attempt < 8; ++attempt) {
-            const size_t chunk_cap = (size_t)np + pool_cap / (GATE_OUTCAP - 32) + 16;
+            const size_t chunk_cap = (size_t)my_np + pool_cap / (GATE_OUTCAP - 32) + 16;
             CKR(ensure(ctx, ctx->pool, pool_cap * 8));
             CKR(ensure(ctx, ctx->chunks, chunk_cap * 16));
-            CK(cudaMemsetAsync(ctx->pair_cnt.p, 0, (np + 1) * 4, st));
+            CK(cudaMemsetAsync(ctx->pair_cnt_s.p, 0, (np + 1) * 4, st));
             CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_WORK, 0, sizeof(unsigned long long), st));
             GateArgs A;
             A.sp0 = ctx->sp0.as<float4>(); A.sp1 = ctx->sp1.as<float4>(); A.sp2 = ctx->sp2.as<float4>();
             A.sp3 = ctx->sp3.as<float4>(); A.cell_start = ctx->cell_start.as<uint32_t>();
-            A.psorted = ctx->psorted.as<uint32_t>(); A.prank = ctx->prank.as<uint32_t>();
-            A.radius = ctx->radius.as<float>(); A.geo = geo; A.g = g; A.np = (int)np;
+            A.pinfo = ctx->pinfo.as<float4>(); A.g = g; A.t_begin = (int)tb[R]; A.t_end = (int)tb[R + 1];
             A.cthr = color_delta * color_delta * 0.5f;           // mixture.cpp:123
             A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
-            A.pair_cnt = ctx->pair_cnt.as<uint32_t>();
+            A.pair_cnt_s = ctx->pair_cnt_s.as<uint32_t>();
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
             A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
             A.counters = ctx->counters.as<unsigned long long>();
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
-            k_gate<<<blocks_for(np, GATE_WARPS), GATE_WARPS * 32, 0, st>>>(A);
-            CK(cudaGetLastError());
+            if (my_np > 0) {
+                k_gate<<<(unsigned)std::min<int64_t>(blocks_for(my_np, GATE_WARPS), (int64_t)ctx->sm_count * 4), GATE_WARPS * 32, 0, st>>>(A);
+                CK(cudaGetLastError());
+                ctx->n_launches++;
+            }
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK1], st));
-            ctx->n_launches++;
+            if (G == 1) {       // single GPU: counts are complete, scan before the one host sync of this stage
+                CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
+                    return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt_s.as<uint32_t>(), ctx->pair_off_s.as<uint32_t>(),
+                                                         (int)(np + 1), st);
+                }));
+            }
             CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                              // sync B
-            if (ctx->h_counters[C_POOL] <= pool_cap && ctx->h_counters[C_CHUNK] <= chunk_cap) break;
+            nchunks = ctx->h_counters[C_CHUNK];
+            if (ctx->h_counters[C_POOL] <= pool_cap && nchunks <= chunk_cap) break;
             pool_cap = (size_t)ctx->h_counters[C_POOL] + (size_t)ctx->h_counters[C_POOL] / 4 + 1024;
             if (attempt == 7) { ctx->err = "pair pool overflow persisted"; return HEM_ERR_STATE; }
         }
-        P = (int64_t)ctx->h_counters[C_POOL];
-        const unsigned long long nchunks = ctx->h_counters[C_CHUNK];
+        std::vector<int64_t> pb(G + 1, 0);          // pair offsets at the slab bounds
+        if (G == 1) {
+            pb[1] = (int64_t)ctx->h_counters[C_POOL];
+        } else {
+            // exchange the per-parent counts, scan them everywhere, fetch the offsets at the slab bounds
+            CKR(allgather_ranges(ctx, ctx->pair_cnt_s.p, 4, tb.data()));
+            CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
+                return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt_s.as<uint32_t>(), ctx->pair_off_s.as<uint32_t>(),
+                                                     (int)(np + 1), st);
+            }));
+            std::vector<uint32_t> hb(G + 1, 0);
+            for (int q = 0; q <= G; ++q)
+                CK(cudaMemcpyAsync(&hb[q], ctx->pair_off_s.as<uint32_t>() + tb[q], 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));                              // sync B2 (multi-GPU only)
+            for (int q = 0; q <= G; ++q) pb[q] = hb[q];
+        }
+        P = pb[G];
         if (P >= (int64_t)1 << 32) { ctx->err = "more than 2^32-1 accepted pairs per level is not supported"; return HEM_ERR_INVALID; }
         S.n_pairs = P;
-        CKR(cub_call(ctx, [&](void* t, size_t& b) {
-            return cub::DeviceScan::ExclusiveSum(t, b, ctx->pair_cnt.as<uint32_t>(), ctx->pair_off.as<uint32_t>(),
-                                                 (int)(np + 1), st);
-        }));
+        CKR(ensure(ctx, ctx->csr_s, std::max<int64_t>(P, 1) * 8));
         CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
         CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
         if (nchunks > 0) {
             k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
-                ctx->chunks.as<uint4>(), nchunks, ctx->pool.as<uint2>(), ctx->pair_off.as<uint32_t>(),
-                ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
+                ctx->chunks.as<uint4>(), nchunks, ctx->pool.as<uint2>(), ctx->pair_off_s.as<uint32_t>(), ctx->csr_s.as<uint2>());
+            CK(cudaGetLastError()); ctx->n_launches++;
+        }
+        CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
+        CK(cudaMemsetAsync(ctx->pair_cnt.p, 0, (np + 1) * 4, st));
+        k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_cnt_s.as<uint32_t>(), (int)np,
+                                                          ctx->pair_cnt.as<uint32_t>());
+        CK(cudaGetLastError()); ctx->n_launches++;
+        CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
+            return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt.as<uint32_t>(), ctx->pair_off.as<uint32_t>(),
+                                                 (int)(np + 1), st);
+        }));
+        if (P > 0) {
+            k_csr_canon<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                                                                   ctx->pair_off.as<uint32_t>(), ctx->csr_s.as<uint2>(), (int)np,
+                                                                   ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
@@ -348,8 +477,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->sk, P * 4));
             CKR(ensure(ctx, ctx->sv, P * 4));
             const int cbits = bits_for((uint64_t)n - 1);
-            CKR(cub_call(ctx, [&](void* t, size_t& b) {
-                return cub::DeviceRadixSort::SortPairs(t, b, ctx->csr_child.as<uint32_t>(), ctx->sk.as<uint32_t>(),
+            CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
+                return cub::DeviceRadixSort::SortPairs(tt, bb, ctx->csr_child.as<uint32_t>(), ctx->sk.as<uint32_t>(),
                                                        ctx->csr_wl.as<float>(), ctx->sv.as<float>(), (int)P, 0, cbits, st);
             }));
             k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P,
@@ -360,16 +489,35 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
 
         // ---- S4 moments -------------------------------------------------------------------------------
         MomArgs M;
-        M.geo = geo; M.sh = sh; M.Fp = Fp; M.psorted = ctx->psorted.as<uint32_t>(); M.sp0 = ctx->sp0.as<float4>();
-        M.prank = ctx->prank.as<uint32_t>(); M.np = (int)np; M.pair_off = ctx->pair_off.as<uint32_t>();
-        M.csr_child = ctx->csr_child.as<uint32_t>(); M.csr_wl = ctx->csr_wl.as<float>(); M.sumlw = ctx->sumlw.as<float>();
-        M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>(); M.valid = ctx->valid.as<uint8_t>();
+        M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = ctx->ptab.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
+        M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = ctx->sumlw.as<float>();
+        M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
         M.seed = ctx->seed; M.rng_base = rng_base; M.pp = pp; M.counters = ctx->counters.as<unsigned long long>();
+        if (G == 1) {
+            M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
+        } else {
+            CKR(ensure(ctx, ctx->stage_geo, (size_t)np * 64));
+            CKR(ensure(ctx, ctx->stage_sh, (size_t)np * std::max(Fp, 1) * 4));
+            M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
+        }
+        CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_WORK, 0, sizeof(unsigned long long), st));
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
-        k_moments<<<blocks_for(np, MOM_WARPS), MOM_WARPS * 32, 0, st>>>(M);
-        CK(cudaGetLastError());
+        if (my_np > 0) {
+            k_moments<<<(unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st>>>(M);
+            CK(cudaGetLastError());
+            ctx->n_launches++;
+        }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK1], st));
-        ctx->n_launches++;
+        if (G > 1) {
+            // all-gather the merged rows (staged in cell order, one contiguous range per rank), then put
+            // them at their canonical place: every rank ends the step with the complete next level
+            CKR(allgather_ranges(ctx, ctx->stage_geo.p, 64, tb.data()));
+            if (Fp > 0) CKR(allgather_ranges(ctx, ctx->stage_sh.p, (size_t)Fp * 4, tb.data()));
+            k_permute_rows<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), (int)np, ctx->stage_geo.as<float4>(),
+                                                                      ctx->stage_sh.as<float>(), Fp, out.geo.as<float4>(),
+                                                                      out.sh.as<float>());
+            CK(cudaGetLastError()); ctx->n_launches++;
+        }
     } else if (ctx->timing) {
         CK(cudaEventRecord(ctx->ev[EV_GRID], st));
         CK(cudaEventRecord(ctx->ev[EV_GATE], st));
@@ -387,8 +535,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     }));
     k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(),
                                                    (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>(),
-                                                   ctx->valid.as<uint8_t>(), ctx->seed, rng_base, pp,
-                                                   ctx->counters.as<unsigned long long>());
+                                                   ctx->seed, rng_base, pp);
+    CK(cudaGetLastError()); ctx->n_launches++;
+    // validity of every pre-filter row (merged parents and orphans): launched over the row capacity,
+    // the actual row count is read on the device, so one host sync closes the step
+    CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_INVALID, 0, sizeof(unsigned long long), st));
+    k_validity<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(),
+                                                           ctx->oflag.as<uint32_t>(), n, ctx->valid.as<uint8_t>(),
+                                                           ctx->counters.as<unsigned long long>());
     CK(cudaGetLastError()); ctx->n_launches++;
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->orank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -509,6 +663,7 @@ hem_ctx* hem_create(int device, uint64_t seed)
         return nullptr;
     }
     ctx->stream = ctx->own_stream;
+    if (const char* cs = getenv("HEM_CELL_SCALE")) { double v = atof(cs); if (v > 0) ctx->cell_scale = v; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
 }
@@ -523,13 +678,14 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
-                      &ctx->pair_cnt, &ctx->pair_off, &ctx->parent_of_rank, &ctx->pool, &ctx->chunks, &ctx->csr_child,
+                      &ctx->pair_cnt, &ctx->pair_off, &ctx->pair_cnt_s, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->sumlw, &ctx->oflag, &ctx->orank, &ctx->valid, &ctx->vflag,
                       &ctx->vpos, &ctx->cubtmp, &ctx->counters, &ctx->prep, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh };
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_prep) cudaFreeHost(ctx->h_prep);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -707,15 +863,37 @@ int hem_get_info(const hem_ctx* ctx, const char* name, double* out)
 
 int hem_nccl_unique_id(uint8_t* id_out)
 {
-    (void)id_out;
-    return HEM_ERR_NCCL;
+    if (!id_out) return HEM_ERR_INVALID;
+    if (!nccl_load()) { g_create_error = g_nccl.err; return HEM_ERR_NCCL; }
+    NcclId id;
+    memset(&id, 0, sizeof id);
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return HEM_ERR_NCCL; }
+    memcpy(id_out, &id, HEM_NCCL_ID_BYTES);
+    return HEM_OK;
 }
 
 int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world)
 {
-    (void)id; (void)rank; (void)world;
-    if (ctx) ctx->err = "multi-GPU communicator not available in this build";
-    return HEM_ERR_NCCL;
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return HEM_ERR_INVALID;
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; return HEM_OK; }
+    if (!nccl_load()) { ctx->err = g_nccl.err; return HEM_ERR_NCCL; }
+    CK(cudaSetDevice(ctx->device));
+    NcclId nid;
+    memcpy(&nid, id, HEM_NCCL_ID_BYTES);
+    void* comm = nullptr;
+    NK(g_nccl.CommInitRank(&comm, world, nid, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return HEM_OK;
+}
+
+int hem_slab_range(int64_t n_parents, int rank, int world, int64_t* begin, int64_t* end)
+{
+    if (world < 1 || rank < 0 || rank >= world || n_parents < 0 || !begin || !end) return HEM_ERR_INVALID;
+    *begin = slab_bound(n_parents, rank, world);
+    *end = slab_bound(n_parents, rank + 1, world);
+    return HEM_OK;
 }
 
 } // extern "C"

@@ -34,12 +34,12 @@ namespace hem {
 //   sp2 = (c00, c01, c02, c11)
 //   sp3 = (c12, c22, det, 0)
 struct GridP {
-    float ox, oy, oz, inv_h;
+    float ox, oy, oz, inv_h, h;     // h = 1/inv_h evaluated in FP32 (cell edge used for row culling)
     int gx, gy, gz;
 };
 
 // device counters (unsigned long long each)
-enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_NPAR = 4, C_COUNT = 8 };
+enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_NPAR = 4, C_WORK = 5, C_COUNT = 8 };
 
 // statistics block written by k_prep
 struct PrepStats {
@@ -136,27 +136,55 @@ __global__ void __launch_bounds__(256)
 k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* __restrict__ radius,
        uint32_t* __restrict__ pflag, PrepStats* __restrict__ stats)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // The FP64 closed-form eigenvalue is ~400 instructions and only one component in
+    // hemReduction is a parent: parents of the block are compacted through shared memory so
+    // that the eigen code runs on full warps.
+    __shared__ float s_cov[256][6];
+    __shared__ uint16_t s_src[256];
+    __shared__ float s_rad[256];
+    __shared__ int s_woff[9];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
     int bmin[3] = { INT_MAX, INT_MAX, INT_MAX }, bmax[3] = { INT_MIN, INT_MIN, INT_MIN };
-    float rad = 0.0f;
-    unsigned int rbits = 0, rcount = 0;
-    double rsum = 0.0;
+    bool flag = false;
+    float4 q1 = make_float4(0, 0, 0, 0), q2 = q1;
     if (i < n) {
-        float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
-        bool flag = (__float_as_uint(q3.w) & 1u) != 0;
+        const float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
+        flag = (__float_as_uint(q3.w) & 1u) != 0;
         pflag[i] = flag ? 1u : 0u;
         if (q0.x == q0.x) { bmin[0] = bmax[0] = f2ord(q0.x); }
         if (q0.y == q0.y) { bmin[1] = bmax[1] = f2ord(q0.y); }
         if (q0.z == q0.z) { bmin[2] = bmax[2] = f2ord(q0.z); }
-        if (flag) {
-            float4 q1 = geo[4 * i + 1], q2 = geo[4 * i + 2];
-            Sym3 c = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
-            rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
-            if (rad > 0.0f && rad < FLT_MAX) { rbits = __float_as_uint(rad); rcount = 1; rsum = (double)rad; }
-        }
-        radius[i] = rad;
+        if (flag) { q1 = geo[4 * i + 1]; q2 = geo[4 * i + 2]; }
     }
-    const unsigned full = 0xffffffffu;
+    s_rad[tid] = 0.0f;
+    const unsigned bal = __ballot_sync(full, flag);
+    if (lane == 0) s_woff[warp + 1] = __popc(bal);
+    __syncthreads();
+    if (tid == 0) {
+        s_woff[0] = 0;
+        for (int w = 0; w < 8; ++w) s_woff[w + 1] += s_woff[w];
+    }
+    __syncthreads();
+    if (flag) {
+        const int slot = s_woff[warp] + __popc(bal & ((1u << lane) - 1u));
+        s_cov[slot][0] = q1.x; s_cov[slot][1] = q1.y; s_cov[slot][2] = q1.z;
+        s_cov[slot][3] = q1.w; s_cov[slot][4] = q2.x; s_cov[slot][5] = q2.y;
+        s_src[slot] = (uint16_t)tid;
+    }
+    __syncthreads();
+    const int npar = s_woff[8];
+    unsigned int rbits = 0, rcount = 0;
+    double rsum = 0.0;
+    if (tid < npar) {
+        const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
+        const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
+        if (rad > 0.0f && rad < FLT_MAX) { rbits = __float_as_uint(rad); rcount = 1; rsum = (double)rad; }
+        s_rad[s_src[tid]] = rad;
+    }
+    __syncthreads();
+    if (i < n) radius[i] = s_rad[tid];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         bmin[a] = __reduce_min_sync(full, bmin[a]);
@@ -166,7 +194,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     rcount = __reduce_add_sync(full, rcount);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (bmin[a] != INT_MAX) atomicMin(&stats->bbmin[a], bmin[a]);
@@ -226,144 +254,204 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
 // that neighbouring warps stream the same cell runs out of L2.
 // ---------------------------------------------------------------------------
 constexpr int GATE_WARPS = 8;
-constexpr int GATE_OUTCAP = 96;
+constexpr int GATE_OUTCAP = 128;
+
+// per-parent record in cell order, built once per step by k_ptab so that a gate warp starts
+// from ONE contiguous 80-byte read instead of a chain of dependent gathers
+//   [0..3] = sp0..sp3 of the parent's slot, [4] = (radius, weight, bits(canonical rank), bits(canonical index))
+constexpr int PINFO_F4 = 5;
 
 struct GateArgs {
     const float4* sp0; const float4* sp1; const float4* sp2; const float4* sp3;
     const uint32_t* cell_start;
-    const uint32_t* psorted;     // [np] sorted slot of each parent, in cell order
-    const uint32_t* prank;       // [n]  canonical parent rank of component i
-    const float* radius;         // [n]
-    const float4* geo;           // canonical rows (parent weight)
+    const float4* pinfo;         // [np * PINFO_F4]
     GridP g;
-    int np;
+    int t_begin, t_end;          // this rank's slab of parents (cell order)
     float cthr, kthr, decay2;
-    uint32_t* pair_cnt;          // [np+1] by canonical parent rank
+    uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
     uint2* pool; unsigned long long pool_cap;
-    uint4* chunks; unsigned long long chunk_cap;
+    uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count, prefix inside the parent)
     unsigned long long* counters;
 };
 
-__global__ void __launch_bounds__(GATE_WARPS * 32)
+__global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __restrict__ sp0,
+                       const float4* __restrict__ sp1, const float4* __restrict__ sp2,
+                       const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
+                       const float* __restrict__ radius, const float4* __restrict__ geo, int np,
+                       uint2* __restrict__ ptab, float4* __restrict__ pinfo)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np) return;
+    const uint32_t pj = psorted[t];
+    const float4 p0 = sp0[pj];
+    const uint32_t s = __float_as_uint(p0.w) & 0x7fffffffu;
+    const uint32_t srank = prank[s];
+    ptab[t] = make_uint2(s, srank);
+    float4* o = pinfo + (size_t)t * PINFO_F4;
+    o[0] = p0; o[1] = sp1[pj]; o[2] = sp2[pj]; o[3] = sp3[pj];
+    o[4] = make_float4(radius[s], geo[4 * (size_t)s].w, __uint_as_float(srank), __uint_as_float(s));
+}
+
+__global__ void __launch_bounds__(GATE_WARPS * 32, 4)
 k_gate(GateArgs A)
 {
     __shared__ uint32_t s_q[GATE_WARPS][64];
-    __shared__ uint2 s_out[GATE_WARPS][GATE_OUTCAP];
+    __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * GATE_WARPS + warp;
-    if (t >= A.np) return;
-
-    const uint32_t pj = A.psorted[t];
-    const float4 p0 = A.sp0[pj], p1 = A.sp1[pj], p2 = A.sp2[pj], p3 = A.sp3[pj];
-    const uint32_t s = __float_as_uint(p0.w) & 0x7fffffffu;
-    const uint32_t srank = A.prank[s];
-    const float rad = A.radius[s];
-    const float pw = A.geo[4 * (size_t)s].w;
-    const float r2 = fm(rad, rad);
-    const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
-    const float pdet = p3.z;
-    const Sym3 ip = inverse_sym3(pc, pdet);
-
     uint32_t* q = s_q[warp];
-    uint2* ob = s_out[warp];
-    int qn = 0, on = 0;
-    uint32_t total = 0;
+    uint32_t* ob = s_out[warp];
+    const float hc = A.g.h;
+    const float INF = __uint_as_float(0x7f800000u);
 
-    auto flush = [&]() {
-        if (on > 0) {
-            unsigned long long base = 0, cid = 0;
-            if (lane == 0) {
-                base = atomicAdd(&A.counters[C_POOL], (unsigned long long)on);
-                cid = atomicAdd(&A.counters[C_CHUNK], 1ull);
-            }
-            base = __shfl_sync(full, base, 0);
-            if (base + (unsigned long long)on <= A.pool_cap)
-                for (int k = lane; k < on; k += 32) A.pool[base + k] = ob[k];
-            if (lane == 0 && cid < A.chunk_cap)
-                A.chunks[cid] = make_uint4(srank, (uint32_t)base, (uint32_t)on, total);
-            total += (uint32_t)on;
-            on = 0;
-            __syncwarp();
-        }
-    };
+    // persistent warps: parents are handed out in cell order through one ticket counter, so
+    // neighbouring warps stream the same cell runs and a heavy parent delays nobody else
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
+        const int t = A.t_begin + (int)__shfl_sync(full, ticket, 0);
+        if (t >= A.t_end) break;
 
-    // candidates that passed the radius + parent-exclusion test: colour gate, KLD gate, likelihood
-    auto process = [&](int m) {
-        bool acc = false;
-        uint32_t cidx = 0;
-        float wl = 0.0f;
-        if (lane < m) {
-            const uint32_t jj = q[lane];
-            const float4 c1 = A.sp1[jj];
-            // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
-            const float cd2 = sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z);
-            const float cdist = __fsqrt_rn(cd2);
-            if (!(cdist > A.cthr)) {
-                const float4 c0 = A.sp0[jj], c2 = A.sp2[jj], c3 = A.sp3[jj];
-                // KLD(child || parent), gaussian.hpp:106-109
-                const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
-                const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
-                const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
-                const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
-                const float smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
-                const float t00 = fa(fa(fm(c2.x, ip.e00), fm(c2.y, ip.e01)), fm(c2.z, ip.e02));
-                const float t11 = fa(fa(fm(c2.y, ip.e01), fm(c2.w, ip.e11)), fm(c3.x, ip.e12));
-                const float t22 = fa(fa(fm(c2.z, ip.e02), fm(c3.x, ip.e12)), fm(c3.y, ip.e22));
-                const float tr = fa(fa(t00, t11), t22);
-                const float cdet = c3.z;
-                const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(cdet, pdet))));
-                if (!(kl > A.kthr)) {
-                    acc = true;
-                    cidx = __float_as_uint(c0.w) & 0x7fffffffu;
+        const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
+        const float4 p0 = pi[0], p1 = pi[1], p2 = pi[2], p3 = pi[3], p4 = pi[4];
+        const uint32_t s = __float_as_uint(p4.w);
+        const float rad = p4.x;
+        const float pw = p4.y;
+        const float r2 = fm(rad, rad);
+        const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
+        const float pdet = p3.z;
+        const Sym3 ip = inverse_sym3(pc, pdet);
+
+        int qn = 0, on = 0;
+        uint32_t total_out = 0;
+
+        // accepted children wait in `ob` as sorted slots; the likelihood is evaluated here, on
+        // compacted lanes, once per flush instead of once per candidate batch
+        auto flush = [&]() {
+            if (on > 0) {
+                unsigned long long base = 0, cid = 0;
+                if (lane == 0) {
+                    base = atomicAdd(&A.counters[C_POOL], (unsigned long long)on);
+                    cid = atomicAdd(&A.counters[C_CHUNK], 1ull);
+                }
+                base = __shfl_sync(full, base, 0);
+                const bool room = base + (unsigned long long)on <= A.pool_cap;
+                for (int k = lane; k < on; k += 32) {
+                    const uint32_t jj = ob[k];
+                    const float4 c0 = A.sp0[jj], c1 = A.sp1[jj];
+                    const float cdet = A.sp3[jj].z;
                     // hemLikelihoodOpacity, mixture.cpp:54-64; clamp + parent weight, :155-156
                     const float dd = __fsqrt_rn(sqdist3(p0.x, p0.y, p0.z, c0.x, c0.y, c0.z));
+                    const float cdist = __fsqrt_rn(sqdist3(p1.x, p1.y, p1.z, c1.x, c1.y, c1.z));
                     const float distWeight = expf(fd(fm(-dd, dd), A.decay2));
                     const float colorInfluence = expf(fd(fm(-cdist, cdist), A.decay2));
                     const float L = fm(fm(fm(distWeight, c1.w), colorInfluence), __fsqrt_rn(cdet));
-                    wl = fm(pw, clamp_ref(L, FLT_MIN, 1e8f));
+                    const float wl = fm(pw, clamp_ref(L, FLT_MIN, 1e8f));
+                    if (room) A.pool[base + k] = make_uint2(__float_as_uint(c0.w) & 0x7fffffffu, __float_as_uint(wl));
+                }
+                if (lane == 0 && cid < A.chunk_cap)
+                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on, total_out);
+                total_out += (uint32_t)on;
+                on = 0;
+                __syncwarp();
+            }
+        };
+
+        // candidates that passed the radius + parent-exclusion test: colour gate, KLD gate, likelihood
+        auto process = [&](int m) {
+            bool acc = false;
+            uint32_t jj = 0;
+            if (lane < m) {
+                jj = q[lane];
+                const float4 c1 = A.sp1[jj];
+                // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
+                const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
+                if (!(cdist > A.cthr)) {
+                    const float4 c0 = A.sp0[jj], c2 = A.sp2[jj], c3 = A.sp3[jj];
+                    // KLD(child || parent), gaussian.hpp:106-109
+                    const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
+                    const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
+                    const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
+                    const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
+                    const float smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
+                    const float t00 = fa(fa(fm(c2.x, ip.e00), fm(c2.y, ip.e01)), fm(c2.z, ip.e02));
+                    const float t11 = fa(fa(fm(c2.y, ip.e01), fm(c2.w, ip.e11)), fm(c3.x, ip.e12));
+                    const float t22 = fa(fa(fm(c2.z, ip.e02), fm(c3.x, ip.e12)), fm(c3.y, ip.e22));
+                    const float tr = fa(fa(t00, t11), t22);
+                    const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(c3.z, pdet))));
+                    acc = !(kl > A.kthr);
                 }
             }
-        }
-        const unsigned am = __ballot_sync(full, acc);
-        if (acc) ob[on + __popc(am & ((1u << lane) - 1u))] = make_uint2(cidx, __float_as_uint(wl));
-        on += __popc(am);
-        __syncwarp();
-        if (on > GATE_OUTCAP - 32) flush();
-    };
+            const unsigned am = __ballot_sync(full, acc);
+            if (acc) ob[on + __popc(am & ((1u << lane) - 1u))] = jj;
+            on += __popc(am);
+            __syncwarp();
+            if (on > GATE_OUTCAP - 32) flush();
+        };
 
-    if (rad > 0.0f) {        // NaN / zero radius: no child can pass `d2 < r*r` (pointindex.cpp:138)
-        // conservative cell range (see DESIGN.md "grid range"): the float test can only pass
-        // for |dx| <= rad*(1+5*2^-24); pad for the rounding of the range ends themselves.
-        const float rr = rad * 1.000001f;
-        const float padx = (fabsf(p0.x) + rr) * 2.4e-7f, pady = (fabsf(p0.y) + rr) * 2.4e-7f,
-                    padz = (fabsf(p0.z) + rr) * 2.4e-7f;
-        const int x0 = cell_axis(p0.x - (rr + padx), A.g.ox, A.g.inv_h, A.g.gx);
-        const int x1 = cell_axis(p0.x + (rr + padx), A.g.ox, A.g.inv_h, A.g.gx);
-        const int y0 = cell_axis(p0.y - (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
-        const int y1 = cell_axis(p0.y + (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
-        const int z0 = cell_axis(p0.z - (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
-        const int z1 = cell_axis(p0.z + (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
-        const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-        const int nrows = ny * nz;
+        if (rad > 0.0f) {        // NaN / zero radius: no child can pass `d2 < r*r` (pointindex.cpp:138)
+            // conservative cell box (DESIGN.md "grid range"): the float test can only pass for
+            // |d| <= rad*(1+5*2^-24) per axis; pads cover the rounding of the range ends themselves
+            const float rr = rad * 1.00001f;
+            const float rr2 = rr * rr;
+            const float pady = (fabsf(p0.y) + rr) * 2.4e-7f, padz = (fabsf(p0.z) + rr) * 2.4e-7f;
+            const int y0 = cell_axis(p0.y - (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
+            const int y1 = cell_axis(p0.y + (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
+            const int z0 = cell_axis(p0.z - (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
+            const int z1 = cell_axis(p0.z + (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
+            const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+            const int nrows = ny * nz;
 
-        for (int rb = 0; rb < nrows; rb += 32) {
-            // each lane prefetches the [begin,end) run of one (y,z) row of cells
-            uint32_t ra = 0, re = 0;
-            const int rrow = rb + lane;
-            if (rrow < nrows) {
-                const int y = y0 + rrow % ny, z = z0 + rrow / ny;
-                const uint32_t base = (uint32_t)((z * A.g.gy + y) * A.g.gx);
-                ra = A.cell_start[base + x0];
-                re = A.cell_start[base + x1 + 1];
-            }
-            const int cnt = min(32, nrows - rb);
-            for (int k = 0; k < cnt; ++k) {
-                const uint32_t a = __shfl_sync(full, ra, k), e = __shfl_sync(full, re, k);
-                for (uint32_t b = a; b < e; b += 32) {
-                    const uint32_t jj = b + lane;
+            for (int rb = 0; rb < nrows; rb += 32) {
+                // one (y,z) row of cells per lane: cull rows the sphere misses, trim the x range of
+                // the others to the chord, fetch the [begin,end) run of slots, then scan the lengths
+                uint32_t ra = 0, len = 0;
+                const int rrow = rb + lane;
+                if (rrow < nrows) {
+                    const int y = y0 + rrow % ny, z = z0 + rrow / ny;
+                    float lo = A.g.oy + (float)y * hc, hi = lo + hc;
+                    float pad = (fabsf(A.g.oy) + fabsf(hi) + hc) * 4e-6f;
+                    lo = (y == 0) ? -INF : lo - pad;
+                    hi = (y == A.g.gy - 1) ? INF : hi + pad;
+                    const float dy = fmaxf(0.0f, fmaxf(lo - p0.y, p0.y - hi));
+                    lo = A.g.oz + (float)z * hc; hi = lo + hc;
+                    pad = (fabsf(A.g.oz) + fabsf(hi) + hc) * 4e-6f;
+                    lo = (z == 0) ? -INF : lo - pad;
+                    hi = (z == A.g.gz - 1) ? INF : hi + pad;
+                    const float dz = fmaxf(0.0f, fmaxf(lo - p0.z, p0.z - hi));
+                    const float d2yz = dy * dy + dz * dz;
+                    if (d2yz <= rr2) {
+                        const float dxm = sqrtf(fmaxf(rr2 - d2yz, 0.0f)) * 1.00001f;
+                        const float padx = (fabsf(p0.x) + dxm) * 2.4e-7f;
+                        const int xa = cell_axis(p0.x - (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx);
+                        const int xb = cell_axis(p0.x + (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx);
+                        const uint32_t base = (uint32_t)((z * A.g.gy + y) * A.g.gx);
+                        ra = A.cell_start[base + xa];
+                        len = A.cell_start[base + xb + 1] - ra;
+                    }
+                }
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(full, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t total = __shfl_sync(full, incl, 31);
+                const uint32_t excl = incl - len;
+
+                // lanes walk the concatenation of the runs, 32 candidates per iteration
+                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                    const uint32_t tt = t0 + lane;
+                    int row = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t v = __shfl_sync(full, incl, row + step - 1);
+                        if (v <= tt) row += step;
+                    }
+                    row = min(row, 31);
+                    const uint32_t jj = __shfl_sync(full, ra, row) + (tt - __shfl_sync(full, excl, row));
                     bool in = false;
-                    if (jj < e) {
+                    if (tt < total) {
                         const float4 c0 = A.sp0[jj];
                         const uint32_t w = __float_as_uint(c0.w);
                         // radius test, pointindex.cpp:138 (query - point); parent exclusion, mixture.cpp:131-133
@@ -384,27 +472,51 @@ k_gate(GateArgs A)
                     }
                 }
             }
+            if (qn > 0) process(qn);
+            flush();
         }
-        if (qn > 0) process(qn);
-        flush();
+        if (lane == 0) A.pair_cnt_s[t] = total_out;
+        __syncwarp();
     }
-    if (lane == 0) A.pair_cnt[srank] = total;
 }
 
-// pool -> CSR in ascending canonical parent order
+// pool -> cell-order CSR (what the moment kernel streams; a rank's slab of parents owns one
+// contiguous segment of it, which is what the ranks exchange)
 __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long long nchunks,
-                             const uint2* __restrict__ pool, const uint32_t* __restrict__ pair_off,
-                             uint32_t* __restrict__ csr_child, float* __restrict__ csr_wl)
+                             const uint2* __restrict__ pool, const uint32_t* __restrict__ pair_off_s,
+                             uint2* __restrict__ csr_s)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= nchunks) return;
     const uint4 ch = chunks[c];
-    const size_t dst = (size_t)pair_off[ch.x] + ch.w;
-    for (uint32_t k = lane; k < ch.z; k += 32) {
-        const uint2 p = pool[(size_t)ch.y + k];
-        csr_child[dst + k] = p.x;
-        csr_wl[dst + k] = __uint_as_float(p.y);
+    const size_t dst = (size_t)pair_off_s[ch.x] + ch.w;
+    for (uint32_t k = lane; k < ch.z; k += 32) csr_s[dst + k] = pool[(size_t)ch.y + k];
+}
+
+// per-parent pair counts from cell order to ascending canonical parent order
+__global__ void k_cnt_canon(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_cnt_s, int np,
+                            uint32_t* __restrict__ pair_cnt)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < np) pair_cnt[ptab[t].y] = pair_cnt_s[t];
+}
+
+// cell-order CSR -> CSR in ascending canonical parent order: the input of the stable sort by
+// child that fixes the sumLw summation order (mixture.cpp:143-163)
+__global__ void k_csr_canon(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
+                            const uint32_t* __restrict__ pair_off, const uint2* __restrict__ csr_s, int np,
+                            uint32_t* __restrict__ csr_child, float* __restrict__ csr_wl)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (t >= np) return;
+    const uint32_t a = pair_off_s[t], e = pair_off_s[t + 1];
+    const size_t dst = pair_off[ptab[t].y];
+    for (uint32_t k = a + lane; k < e; k += 32) {
+        const uint2 p = csr_s[k];
+        csr_child[dst + (k - a)] = p.x;
+        csr_wl[dst + (k - a)] = __uint_as_float(p.y);
     }
 }
 
@@ -423,15 +535,29 @@ __global__ void k_segsum(const uint32_t* __restrict__ key, const float* __restri
 }
 
 // ---------------------------------------------------------------------------
-// S4: fused parent moments.  One warp per parent.  mixture.cpp:168-247
+// S4: fused parent moments.  mixture.cpp:168-247
+//
+// Latency-bound gather: every accepted pair pulls the child's 64-byte geometry row and its SH
+// row (192 B at SH degree 3) from the canonical store.  Persistent warps take tickets of
+// MOM_B consecutive parents in cell order, whose pairs are contiguous in the cell-order CSR:
+//   phase 1 (lane = pair)  : child index, wL, sumLw[child], child weight -> w = wL/sumLw * weight
+//   phase 2 (warp = row)   : 8 pairs at a time, all row loads issued first (geometry row by
+//                            lanes 0..15, SH row by the whole warp, coalesced), then accumulated
+//                            in list order; lane j owns element j of the geometry row
+//   parent boundary        : normalise, det, flag, validity, one 64-byte + one SH row store
 // ---------------------------------------------------------------------------
 constexpr int MOM_WARPS = 8;
+constexpr int MOM_B = 8;
 
 struct MomArgs {
     const float4* geo; const float* sh; int Fp;
-    const uint32_t* psorted; const float4* sp0; const uint32_t* prank; int np;
-    const uint32_t* pair_off; const uint32_t* csr_child; const float* csr_wl; const float* sumlw;
-    float4* ogeo; float* osh; uint8_t* valid;
+    const uint2* ptab;            // [np] (canonical index, canonical rank) in cell order
+    const uint32_t* pair_off_s;   // [np+1] cell-order CSR offsets
+    const uint2* csr_s;           // [P] (child, wL bits) in cell order
+    const float* sumlw;
+    int t_begin, t_end;           // this rank's slab of parents (cell order)
+    int by_rank;                  // 1: row index = canonical rank (final place); 0: row index = t (staging for the exchange)
+    float4* ogeo; float* osh;
     uint64_t seed, rng_base; float pp;
     unsigned long long* counters;
 };
@@ -440,99 +566,116 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
 k_moments(MomArgs A)
 {
     const unsigned full = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * MOM_WARPS + warp;
-    if (t >= A.np) return;
-    const uint32_t s = __float_as_uint(A.sp0[A.psorted[t]].w) & 0x7fffffffu;
-    const uint32_t srank = A.prank[s];
-    const uint32_t a = A.pair_off[srank], b = A.pair_off[srank + 1];
-    const float4 pq0 = A.geo[4 * (size_t)s];
+    const int lane = threadIdx.x & 31;
     const int Fp = A.Fp;
+    const float* geof = reinterpret_cast<const float*>(A.geo);
+    float* ogeof = reinterpret_cast<float*>(A.ogeo);
+    // lane j of the low half owns float j of a 64-byte geometry row:
+    //  0 mx 1 my 2 mz 3 weight | 4 c00 5 c01 6 c02 7 c11 | 8 c12 9 c22 10 opacity 11 det | 12 r 13 g 14 b 15 flag
+    const int j = lane & 15;
+    const bool is_cov = j >= 4 && j <= 9;
+    const int sa = (j <= 6) ? 0 : (j <= 8 ? 1 : 2);                 // first index of the outer-product term
+    const int sb = (j == 4) ? 0 : ((j == 5 || j == 7) ? 1 : 2);     // second index
 
-    float acc[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) acc[i] = 0.0f;
-    float sh0 = 0.0f, sh1 = 0.0f;
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
+        const int tb = A.t_begin + (int)__shfl_sync(full, ticket, 0) * MOM_B;
+        if (tb >= A.t_end) break;
+        const int nb = min(MOM_B, A.t_end - tb);
+        const uint32_t off = (lane <= nb) ? A.pair_off_s[tb + lane] : 0xffffffffu;
+        const uint2 pt = (lane < nb) ? A.ptab[tb + lane] : make_uint2(0u, 0u);
+        float4 pq0 = make_float4(0, 0, 0, 0);
+        if (lane < nb) pq0 = A.geo[4 * (size_t)pt.x];               // parent means (outer-product origin)
+        const uint32_t pa = __shfl_sync(full, off, 0), pb = __shfl_sync(full, off, nb);
 
-    for (uint32_t k0 = a; k0 < b; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        uint32_t ch = 0;
-        float w = 0.0f;
-        float tm[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) tm[i] = 0.0f;
-        if (k < b) {
-            ch = A.csr_child[k];
-            const float wl = A.csr_wl[k];
-            const float sl = A.sumlw[ch];
-            const float4 q0 = A.geo[4 * (size_t)ch], q1 = A.geo[4 * (size_t)ch + 1],
-                         q2 = A.geo[4 * (size_t)ch + 2], q3 = A.geo[4 * (size_t)ch + 3];
-            w = fm(fd(wl, sl), q0.w);                       // r_is * child.weight, mixture.cpp:196-197
-            const float dx = q0.x - pq0.x, dy = q0.y - pq0.y, dz = q0.z - pq0.z;
-            tm[0] = w;
-            tm[1] = w * q0.x; tm[2] = w * q0.y; tm[3] = w * q0.z;
-            tm[4] = w * q3.x; tm[5] = w * q3.y; tm[6] = w * q3.z;
-            tm[7] = w * (q1.x + dx * dx); tm[8] = w * (q1.y + dx * dy); tm[9] = w * (q1.z + dx * dz);
-            tm[10] = w * (q1.w + dy * dy); tm[11] = w * (q2.x + dy * dz); tm[12] = w * (q2.y + dz * dz);
-            tm[13] = w * q2.z;
+        int cur = 0;                                                 // parent of the batch being accumulated
+        uint32_t nextb = __shfl_sync(full, off, 1);
+        float pmj = 0.0f;                                            // parent mean component of lanes 0..2
+        {
+            const float x = __shfl_sync(full, pq0.x, 0), y = __shfl_sync(full, pq0.y, 0), z = __shfl_sync(full, pq0.z, 0);
+            pmj = (j == 0) ? x : (j == 1 ? y : (j == 2 ? z : 0.0f));
         }
-#pragma unroll
-        for (int i = 0; i < 14; ++i) {
-            float v = tm[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
-            acc[i] += v;
-        }
-        // SH rows: the whole warp reads one child's row (coalesced), children in list order
-        const int cnt = (int)min(32u, b - k0);
-        int c = 0;
-        for (; c + 4 <= cnt; c += 4) {
-            float wc[4], v0[4], v1[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                wc[u] = __shfl_sync(full, w, c + u);
-                const uint32_t cc = __shfl_sync(full, ch, c + u);
-                const float* row = A.sh + (size_t)cc * Fp;
-                v0[u] = lane < Fp ? row[lane] : 0.0f;
-                v1[u] = lane + 32 < Fp ? row[lane + 32] : 0.0f;
+        float accg = 0.0f, sh0 = 0.0f, sh1 = 0.0f;
+
+        auto finalize = [&]() {
+            // normalise, mixture.cpp:219-226
+            const float w_s = __shfl_sync(full, accg, 3);
+            const float inv_w = fd(1.0f, w_s);
+            const float scaled = fm(inv_w, accg);
+            const float dm = fs(scaled, pmj);                        // mean - parent mean on lanes 0..2
+            const float da = __shfl_sync(full, dm, sa), db = __shfl_sync(full, dm, sb);
+            float outv = is_cov ? fs(scaled, fm(da, db)) : scaled;
+            Sym3 cv;
+            cv.e00 = __shfl_sync(full, outv, 4); cv.e01 = __shfl_sync(full, outv, 5); cv.e02 = __shfl_sync(full, outv, 6);
+            cv.e11 = __shfl_sync(full, outv, 7); cv.e12 = __shfl_sync(full, outv, 8); cv.e22 = __shfl_sync(full, outv, 9);
+            const float dt = det_sym3(cv);
+            const uint32_t srank = __shfl_sync(full, pt.y, cur);
+            // pre-filter position of a merged parent = its rank; flag drawn there, mixture.cpp:257-259
+            const bool flag = parent_flag(A.seed, A.rng_base + (uint64_t)srank, A.pp);
+            if (j == 3) outv = w_s;
+            if (j == 11) outv = dt;
+            if (j == 15) outv = __uint_as_float(flag ? 1u : 0u);
+            const size_t orow_i = A.by_rank ? (size_t)srank : (size_t)(tb + cur);
+            if (lane < 16) ogeof[16 * orow_i + lane] = outv;
+            float* orow = A.osh + orow_i * Fp;
+            if (lane < Fp) orow[lane] = fm(inv_w, sh0);
+            if (lane + 32 < Fp) orow[lane + 32] = fm(inv_w, sh1);
+        };
+        auto advance = [&]() {
+            finalize();
+            ++cur;
+            accg = 0.0f; sh0 = 0.0f; sh1 = 0.0f;
+            if (cur < nb) {
+                nextb = __shfl_sync(full, off, cur + 1);
+                const float x = __shfl_sync(full, pq0.x, cur), y = __shfl_sync(full, pq0.y, cur), z = __shfl_sync(full, pq0.z, cur);
+                pmj = (j == 0) ? x : (j == 1 ? y : (j == 2 ? z : 0.0f));
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { sh0 = fmaf(v0[u], wc[u], sh0); sh1 = fmaf(v1[u], wc[u], sh1); }
-        }
-        for (; c < cnt; ++c) {
-            const float wc = __shfl_sync(full, w, c);
-            const uint32_t cc = __shfl_sync(full, ch, c);
-            const float* row = A.sh + (size_t)cc * Fp;
-            if (lane < Fp) sh0 = fmaf(row[lane], wc, sh0);
-            if (lane + 32 < Fp) sh1 = fmaf(row[lane + 32], wc, sh1);
-        }
-    }
+        };
 
-    // normalise, mixture.cpp:219-226
-    const float inv_w = fd(1.0f, acc[0]);
-    const float mx = inv_w * acc[1], my = inv_w * acc[2], mz = inv_w * acc[3];
-    const float dmx = mx - pq0.x, dmy = my - pq0.y, dmz = mz - pq0.z;
-    Sym3 cv;
-    cv.e00 = fs(fm(inv_w, acc[7]), fm(dmx, dmx)); cv.e01 = fs(fm(inv_w, acc[8]), fm(dmx, dmy));
-    cv.e02 = fs(fm(inv_w, acc[9]), fm(dmx, dmz)); cv.e11 = fs(fm(inv_w, acc[10]), fm(dmy, dmy));
-    cv.e12 = fs(fm(inv_w, acc[11]), fm(dmy, dmz)); cv.e22 = fs(fm(inv_w, acc[12]), fm(dmz, dmz));
-    const float dt = det_sym3(cv);
-    // pre-filter position of a merged parent = its rank; flag drawn there, mixture.cpp:257-259
-    const bool flag = parent_flag(A.seed, A.rng_base + (uint64_t)srank, A.pp);
-    float4 o;
-    if (lane == 0) o = make_float4(mx, my, mz, acc[0]);
-    else if (lane == 1) o = make_float4(cv.e00, cv.e01, cv.e02, cv.e11);
-    else if (lane == 2) o = make_float4(cv.e12, cv.e22, inv_w * acc[13], dt);
-    else o = make_float4(inv_w * acc[4], inv_w * acc[5], inv_w * acc[6], __uint_as_float(flag ? 1u : 0u));
-    if (lane < 4) A.ogeo[4 * (size_t)srank + lane] = o;
-    float* orow = A.osh + (size_t)srank * Fp;
-    if (lane < Fp) orow[lane] = inv_w * sh0;
-    if (lane + 32 < Fp) orow[lane + 32] = inv_w * sh1;
-    if (lane == 0) {
-        // validity filter predicate, mixture.cpp:268-270
-        const bool bad = (mx != mx || my != my || mz != mz) || (dt != dt) || dt <= 0.0f;
-        A.valid[srank] = bad ? 0 : 1;
-        if (bad) atomicAdd(&A.counters[C_INVALID], 1ull);
+        for (uint32_t k0 = pa; k0 < pb; k0 += 32) {
+            // phase 1: one pair per lane
+            const uint32_t k = k0 + lane;
+            uint32_t ch = 0;
+            float w = 0.0f;
+            if (k < pb) {
+                const uint2 pr = A.csr_s[k];
+                ch = pr.x;
+                const float sl = A.sumlw[ch];
+                const float cw = geof[16 * (size_t)ch + 3];
+                w = fm(fd(__uint_as_float(pr.y), sl), cw);             // r_is * child.weight, mixture.cpp:196-197
+            }
+            const int cnt = (int)min(32u, pb - k0);
+            // phase 2: rows, 8 pairs in flight
+            for (int g = 0; g < cnt; g += 8) {
+                float gv[8], v0[8], v1[8], wc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = min(g + u, cnt - 1);
+                    const uint32_t cc = __shfl_sync(full, ch, c);
+                    wc[u] = __shfl_sync(full, w, c);
+                    gv[u] = geof[16 * (size_t)cc + j];
+                    const float* row = A.sh + (size_t)cc * Fp;
+                    v0[u] = lane < Fp ? row[lane] : 0.0f;
+                    v1[u] = lane + 32 < Fp ? row[lane + 32] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (g + u < cnt) {                                  // uniform
+                        while (k0 + g + u == nextb && cur < nb - 1) advance();   // parent boundary (empty parents too)
+                        const float dv = fs(gv[u], pmj);
+                        const float da = __shfl_sync(full, dv, sa), db = __shfl_sync(full, dv, sb);
+                        const float val = (j == 3) ? 1.0f : (is_cov ? fa(gv[u], fm(da, db)) : gv[u]);
+                        accg = fa(accg, fm(wc[u], val));
+                        sh0 = fa(sh0, fm(v0[u], wc[u]));
+                        sh1 = fa(sh1, fm(v1[u], wc[u]));
+                    }
+                }
+            }
+        }
+        while (cur < nb - 1) advance();      // trailing parents without pairs
+        finalize();
+        __syncwarp();
     }
 }
 
@@ -548,8 +691,8 @@ __global__ void k_orphan_flag(const float* __restrict__ sumlw, int64_t n, uint32
 __global__ void __launch_bounds__(256)
 k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, int64_t n,
           const uint32_t* __restrict__ oflag, const uint32_t* __restrict__ orank, uint32_t np,
-          float4* __restrict__ ogeo, float* __restrict__ osh, uint8_t* __restrict__ valid,
-          uint64_t seed, uint64_t rng_base, float pp, unsigned long long* counters)
+          float4* __restrict__ ogeo, float* __restrict__ osh,
+          uint64_t seed, uint64_t rng_base, float pp)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -566,21 +709,45 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
         const size_t dst = (size_t)np + __shfl_sync(full, myrank, src);
         float4 v;
         if (lane < 4) v = geo[4 * (size_t)ci + lane];
-        // lanes 0..3 hold q0..q3; validity needs q0 (mean) and q2.w (det)
-        const float mx = __shfl_sync(full, v.x, 0), my = __shfl_sync(full, v.y, 0), mz = __shfl_sync(full, v.z, 0);
-        const float dt = __shfl_sync(full, v.w, 2);
         if (lane == 3) v.w = __uint_as_float(parent_flag(seed, rng_base + (uint64_t)dst, pp) ? 1u : 0u);
         if (lane < 4) ogeo[4 * dst + lane] = v;
         const float* srow = sh + (size_t)ci * Fp;
         float* drow = osh + dst * Fp;
         if (lane < Fp) drow[lane] = srow[lane];
         if (lane + 32 < Fp) drow[lane + 32] = srow[lane + 32];
-        if (lane == 0) {
-            const bool bad = (mx != mx || my != my || mz != mz) || (dt != dt) || dt <= 0.0f;
-            valid[dst] = bad ? 0 : 1;
-            if (bad) atomicAdd(&counters[C_INVALID], 1ull);
-        }
     }
+}
+
+// validity filter predicate on every pre-filter output row, mixture.cpp:262-270
+__global__ void k_validity(const float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
+                           const uint32_t* __restrict__ oflag, int64_t n_in, uint8_t* __restrict__ valid,
+                           unsigned long long* __restrict__ counters)
+{
+    // pre-filter row count = parents + orphans, read on the device (the host learns it afterwards)
+    const int64_t n = np + (int64_t)orank[n_in - 1] + (int64_t)oflag[n_in - 1];
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (j < n) {
+        const float4 q0 = geo[4 * j];
+        const float dt = geo[4 * j + 2].w;
+        bad = (q0.x != q0.x || q0.y != q0.y || q0.z != q0.z) || (dt != dt) || dt <= 0.0f;
+        valid[j] = bad ? 0 : 1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[C_INVALID], (unsigned long long)__popc(m));
+}
+
+// staged merged rows (index = cell-order position t) -> their final place (index = canonical rank)
+__global__ void k_permute_rows(const uint2* __restrict__ ptab, int np, const float4* __restrict__ sgeo,
+                               const float* __restrict__ ssh, int Fp, float4* __restrict__ ogeo,
+                               float* __restrict__ osh)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (t >= np) return;
+    const size_t d = ptab[t].y;
+    if (lane < 4) ogeo[4 * d + lane] = sgeo[4 * (size_t)t + lane];
+    for (int q = lane; q < Fp; q += 32) osh[d * Fp + q] = ssh[(size_t)t * Fp + q];
 }
 
 __global__ void k_valid_flag(const uint8_t* __restrict__ valid, int64_t n, uint32_t* __restrict__ out)

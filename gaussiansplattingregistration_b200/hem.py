@@ -44,6 +44,40 @@ def _ptr(x):
     return C.c_void_p(a.ctypes.data), a
 
 
+def slab_range(n_parents: int, rank: int, world: int) -> tuple[int, int]:
+    """Parents (positions in grid-cell order) [begin, end) owned by `rank` — host arithmetic only."""
+    lib = _capi.load()
+    b, e = C.c_int64(0), C.c_int64(0)
+    rc = lib.hem_slab_range(int(n_parents), int(rank), int(world), C.byref(b), C.byref(e))
+    if rc != 0:
+        raise _capi.HemError(rc, "bad slab_range arguments")
+    return int(b.value), int(e.value)
+
+
+def nccl_unique_id() -> bytes:
+    lib = _capi.load()
+    buf = (C.c_uint8 * _capi.NCCL_ID_BYTES)()
+    rc = lib.hem_nccl_unique_id(buf)
+    if rc != 0:
+        msg = lib.hem_last_error(None)
+        raise _capi.HemError(rc, msg.decode() if msg else "hem_nccl_unique_id failed")
+    return bytes(buf)
+
+
+def exchange_unique_id(rank=None, world=None, make_id=nccl_unique_id):
+    """Rank 0 creates the id, everyone receives it through torch.distributed (gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(_capi.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(make_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes()), rank, world
+
+
 class HemContext:
     """One context per GPU (``hem_create`` / ``hem_destroy``)."""
 
@@ -55,6 +89,7 @@ class HemContext:
             raise _capi.HemError(-3, msg.decode() if msg else "hem_create failed")
         self.device = device
         self.sh_floats = 0
+        self.rank, self.world = 0, 1
 
     # -- plumbing -----------------------------------------------------------
     def _check(self, code: int):
@@ -84,6 +119,17 @@ class HemContext:
 
     def set_stream(self, stream_handle: int | None):
         self._check(self._lib.hem_set_stream(self._h, C.c_void_p(stream_handle or 0)))
+
+    # -- multi-GPU ------------------------------------------------------------------
+    def init_distributed(self, rank: int | None = None, world: int | None = None, unique_id: bytes | None = None):
+        """Join the NCCL communicator of a one-process-per-GPU job.  With
+        no arguments the rank/world come from ``torch.distributed`` (already
+        initialised, any backend) and rank 0's NCCL unique id is broadcast through it."""
+        if unique_id is None:
+            unique_id, rank, world = exchange_unique_id(rank, world)
+        buf = (C.c_uint8 * _capi.NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.hem_comm_init(self._h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
 
     # -- the hot path ----------------------------------------------------------
     def build(self, xyz, colors, opacity, cov6, sh, cluster_level: int, hem_reduction: float = 3.0,

@@ -136,10 +136,15 @@ int hem_step_pairs(hem_ctx* ctx, int step, uint32_t* parent_idx, int64_t* off,
 int hem_nccl_unique_id(uint8_t* id_out);
 
 /* Join a communicator of `world` ranks.  After this, hem_build_pyramid must be
- * called collectively with identical arguments on every rank; each rank
- * processes the parents of its slab and every level's reduced set is
- * all-gathered, so every rank ends with the complete pyramid. */
+ * called collectively with identical arguments (and identical input arrays) on
+ * every rank; each rank runs the gate and moment kernels for the parents of its
+ * slab, the accepted pairs and the merged rows are all-gathered per level, so
+ * every rank ends with the complete pyramid, bit-identical to a 1-GPU run. */
 int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world);
+
+/* Pure host arithmetic, no GPU needed: the slab of parents (positions in grid-cell order)
+ * [*begin, *end) that rank `rank` of `world` owns when a level has n_parents parents. */
+int hem_slab_range(int64_t n_parents, int rank, int world, int64_t* begin, int64_t* end);
 
 /* Library/ABI version (major*1000 + minor). */
 int hem_version(void);
