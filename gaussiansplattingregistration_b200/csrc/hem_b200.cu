@@ -34,8 +34,9 @@ struct DevBuf {
 
 struct Level {
     int64_t n = 0;
-    DevBuf geo;    // float4[4*cap]
-    DevBuf sh;     // float[cap*Fp]
+    DevBuf geo;              // float4[4*cap]
+    DevBuf sh;               // float[cap*F], owned storage
+    const float* shp = nullptr;   // where the SH rows are: sh.p, or the caller's device array (level 0, in place)
 };
 
 struct StepStats {
@@ -60,7 +61,7 @@ struct hem_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     bool timing = false, keep_pairs = false;
-    double cell_scale = 1.0;
+    double cell_scale = 0.5;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
     int F = 0, Fp = 0;
@@ -261,7 +262,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     if (n >= (int64_t)1 << 31) { ctx->err = "more than 2^31-1 components per level is not supported"; return HEM_ERR_INVALID; }
 
     const float4* geo = in.geo.as<float4>();
-    const float* sh = in.sh.as<float>();
+    const float* sh = in.shp;
 
     // ---- S1 prep --------------------------------------------------------------------------
     CKR(ensure(ctx, ctx->radius, n * 4));
@@ -277,7 +278,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CK(cudaMemcpyAsync(ctx->prep.p, ctx->h_prep, sizeof(PrepStats), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long), st));
     }
-    k_prep<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, distance_delta, ctx->radius.as<float>(),
+    k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(geo, n, distance_delta, ctx->radius.as<float>(),
                                                 ctx->pflag.as<uint32_t>(), ctx->prep.as<PrepStats>());
     CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
@@ -303,6 +304,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     const int64_t cap_rows = n + np;
     CKR(ensure(ctx, out.geo, (size_t)cap_rows * 64));
     CKR(ensure(ctx, out.sh, (size_t)cap_rows * std::max(Fp, 1) * 4));
+    out.shp = out.sh.as<float>();
     CKR(ensure(ctx, ctx->valid, cap_rows));
     CKR(ensure(ctx, ctx->sumlw, n * 4));
     CK(cudaMemsetAsync(ctx->sumlw.p, 0, n * 4, st));
@@ -492,7 +494,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = ctx->ptab.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
         M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = ctx->sumlw.as<float>();
         M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
-        M.seed = ctx->seed; M.rng_base = rng_base; M.pp = pp; M.counters = ctx->counters.as<unsigned long long>();
+        M.counters = ctx->counters.as<unsigned long long>();
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
@@ -534,15 +536,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(), (int)n, st);
     }));
     k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(),
-                                                   (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>(),
-                                                   ctx->seed, rng_base, pp);
+                                                   (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
     CK(cudaGetLastError()); ctx->n_launches++;
-    // validity of every pre-filter row (merged parents and orphans): launched over the row capacity,
+    // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
     CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_INVALID, 0, sizeof(unsigned long long), st));
-    k_validity<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(),
-                                                           ctx->oflag.as<uint32_t>(), n, ctx->valid.as<uint8_t>(),
-                                                           ctx->counters.as<unsigned long long>());
+    k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(),
+                                                         ctx->oflag.as<uint32_t>(), n, ctx->seed, rng_base, pp,
+                                                         ctx->valid.as<uint8_t>(), ctx->counters.as<unsigned long long>());
     CK(cudaGetLastError()); ctx->n_launches++;
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->orank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -723,7 +724,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->F = sh_floats;
-    ctx->Fp = (sh_floats + 3) / 4 * 4;
+    ctx->Fp = sh_floats;          // rows are stored unpadded
     const int Fp = ctx->Fp;
     if (ctx->levels.size() < (size_t)cluster_level + 1) ctx->levels.resize((size_t)cluster_level + 1);
     for (Level& L : ctx->levels) L.n = 0;
@@ -734,23 +735,29 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     Level& L0 = ctx->levels[0];
     L0.n = n;
     if (n > 0) {
-        const void *dx, *dc, *dop, *dcv, *dsh, *dw, *dm;
+        const void *dx, *dc, *dop, *dcv, *dw, *dm;
         CKR(to_device(ctx, xyz, (size_t)n * 12, ctx->in_xyz, &dx));
         CKR(to_device(ctx, color, (size_t)n * 12, ctx->in_col, &dc));
         CKR(to_device(ctx, opacity, (size_t)n * 4, ctx->in_op, &dop));
         CKR(to_device(ctx, cov6, (size_t)n * 24, ctx->in_cov, &dcv));
-        CKR(to_device(ctx, sh_floats ? sh : nullptr, (size_t)n * sh_floats * 4, ctx->in_sh, &dsh));
         CKR(to_device(ctx, weight, (size_t)n * 4, ctx->in_w, &dw));
         CKR(to_device(ctx, level0_parent_mask, (size_t)n, ctx->in_mask, &dm));
         CKR(ensure(ctx, L0.geo, (size_t)n * 64));
-        CKR(ensure(ctx, L0.sh, (size_t)n * std::max(Fp, 1) * 4));
         k_import<<<blocks_for(n, 256), 256, 0, st>>>((const float*)dx, (const float*)dc, (const float*)dop,
                                                       (const float*)dcv, (const float*)dw, (const uint8_t*)dm,
                                                       L0.geo.as<float4>(), n, ctx->seed, 1.0f / hem_reduction);
         CK(cudaGetLastError()); ctx->n_launches++;
-        if (Fp > 0) {
-            k_pad_sh<<<blocks_for(n * Fp, 256), 256, 0, st>>>((const float*)dsh, L0.sh.as<float>(), n, sh_floats, Fp);
-            CK(cudaGetLastError()); ctx->n_launches++;
+        // SH rows keep the caller's [N,F] layout: a device array is used in place (no copy at all),
+        // a host array is DMA'd straight into the level store
+        if (Fp > 0 && is_device_ptr(sh)) {
+            L0.shp = sh;
+        } else {
+            CKR(ensure(ctx, L0.sh, (size_t)n * std::max(Fp, 1) * 4));
+            L0.shp = L0.sh.as<float>();
+            if (Fp > 0) {
+                CK(cudaMemcpyAsync(L0.sh.p, sh, (size_t)n * Fp * 4, cudaMemcpyHostToDevice, st));
+                ctx->bytes_h2d += (size_t)n * Fp * 4;
+            }
         }
     }
     uint64_t base = ctx->rng_base_set ? ctx->rng_base : (uint64_t)n;
@@ -791,33 +798,32 @@ int hem_level_copy(hem_ctx* ctx, int level, float* xyz, float* color, float* opa
     Level& L = ctx->levels[level];
     const int64_t n = L.n;
     if (n == 0) return HEM_OK;
-    const int F = ctx->F, Fp = ctx->Fp;
-    void *dx, *dc, *dop, *dcv, *dsh, *dw, *df;
-    bool sx, sc, sop, scv, ssh, sw, sf;
+    const int F = ctx->F;
+    void *dx, *dc, *dop, *dcv, *dw, *df;
+    bool sx, sc, sop, scv, sw, sf;
     CKR(from_device(ctx, xyz, (size_t)n * 12, ctx->out_a, &dx, &sx));
     CKR(from_device(ctx, color, (size_t)n * 12, ctx->out_b, &dc, &sc));
     CKR(from_device(ctx, opacity, (size_t)n * 4, ctx->out_c, &dop, &sop));
     CKR(from_device(ctx, cov6, (size_t)n * 24, ctx->out_d, &dcv, &scv));
-    CKR(from_device(ctx, F ? sh : nullptr, (size_t)n * F * 4, ctx->out_e, &dsh, &ssh));
     CKR(from_device(ctx, weight, (size_t)n * 4, ctx->out_f, &dw, &sw));
     CKR(from_device(ctx, is_parent, (size_t)n, ctx->out_g, &df, &sf));
     k_export<<<blocks_for(n, 256), 256, 0, st>>>(L.geo.as<float4>(), n, (float*)dx, (float*)dc, (float*)dop, (float*)dcv,
                                                   (float*)dw, (uint8_t*)df);
     CK(cudaGetLastError()); ctx->n_launches++;
-    if (dsh) {
-        k_unpad_sh<<<blocks_for(n * F, 256), 256, 0, st>>>(L.sh.as<float>(), (float*)dsh, n, F, Fp);
-        CK(cudaGetLastError()); ctx->n_launches++;
+    if (sh && F > 0) {       // rows are stored in the caller's layout: plain DMA (D2H or D2D)
+        const bool to_dev = is_device_ptr(sh);
+        CK(cudaMemcpyAsync(sh, L.shp, (size_t)n * F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (!to_dev) ctx->bytes_d2h += (size_t)n * F * 4;
     }
     if (sx) CK(cudaMemcpyAsync(xyz, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     if (sc) CK(cudaMemcpyAsync(color, dc, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     if (sop) CK(cudaMemcpyAsync(opacity, dop, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (scv) CK(cudaMemcpyAsync(cov6, dcv, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-    if (ssh) CK(cudaMemcpyAsync(sh, dsh, (size_t)n * F * 4, cudaMemcpyDeviceToHost, st));
     if (sw) CK(cudaMemcpyAsync(weight, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (sf) CK(cudaMemcpyAsync(is_parent, df, (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->bytes_d2h += (sx ? (size_t)n * 12 : 0) + (sc ? (size_t)n * 12 : 0) + (sop ? (size_t)n * 4 : 0) +
-                      (scv ? (size_t)n * 24 : 0) + (ssh ? (size_t)n * F * 4 : 0) + (sw ? (size_t)n * 4 : 0) + (sf ? (size_t)n : 0);
+                      (scv ? (size_t)n * 24 : 0) + (sw ? (size_t)n * 4 : 0) + (sf ? (size_t)n : 0);
     return HEM_OK;
 }
 

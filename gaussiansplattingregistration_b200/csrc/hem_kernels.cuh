@@ -26,8 +26,8 @@ namespace hem {
 //         q1 = (c00, c01, c02, c11)
 //         q2 = (c12, c22, opacity, det(cov))
 //         q3 = (col.r, col.g, col.b, is_parent as uint bits)
-//   sh  : Fp floats per component, Fp = F rounded up to a multiple of 4 (16-byte rows,
-//         192 B = six full 32-byte sectors at SH degree 3)
+//   sh  : F floats per component, unpadded (180-byte rows at SH degree 3), exactly the caller's
+//         [N,F] layout: a device-resident input is used in place and levels are copied out by DMA
 // Cell-sorted working set of a step (index = slot in cell order), SoA float4 planes:
 //   sp0 = (mean.x, mean.y, mean.z, bits(canonical index | is_parent << 31))
 //   sp1 = (col.r, col.g, col.b, opacity)
@@ -93,24 +93,6 @@ __global__ void k_import(const float* __restrict__ xyz, const float* __restrict_
     geo[4 * i + 3] = make_float4(col[3 * i], col[3 * i + 1], col[3 * i + 2], __uint_as_float(flag ? 1u : 0u));
 }
 
-__global__ void k_pad_sh(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int F, int Fp)
-{
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n * Fp) return;
-    int64_t i = e / Fp;
-    int q = (int)(e - i * Fp);
-    dst[e] = q < F ? src[i * F + q] : 0.0f;
-}
-
-__global__ void k_unpad_sh(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int F, int Fp)
-{
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n * F) return;
-    int64_t i = e / F;
-    int q = (int)(e - i * F);
-    dst[e] = src[i * Fp + q];
-}
-
 __global__ void k_export(const float4* __restrict__ geo, int64_t n, float* __restrict__ xyz,
                          float* __restrict__ col, float* __restrict__ op, float* __restrict__ cov6,
                          float* __restrict__ weight, uint8_t* __restrict__ flag)
@@ -136,55 +118,63 @@ __global__ void __launch_bounds__(256)
 k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* __restrict__ radius,
        uint32_t* __restrict__ pflag, PrepStats* __restrict__ stats)
 {
-    // The FP64 closed-form eigenvalue is ~400 instructions and only one component in
-    // hemReduction is a parent: parents of the block are compacted through shared memory so
-    // that the eigen code runs on full warps.
+    // * The FP64 closed-form eigenvalue is ~400 instructions and only one component in
+    //   hemReduction is a parent: the parents of a 256-component tile are compacted through
+    //   shared memory so that the eigen code runs on full warps.
+    // * Grid-stride over tiles with the statistics kept in registers: one set of atomics per
+    //   BLOCK at the end (per-warp atomics on nine shared addresses serialised the whole kernel).
     __shared__ float s_cov[256][6];
     __shared__ uint16_t s_src[256];
     __shared__ float s_rad[256];
     __shared__ int s_woff[9];
+    __shared__ int s_red[8][8];
+    __shared__ double s_redd[8];
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
     int bmin[3] = { INT_MAX, INT_MAX, INT_MAX }, bmax[3] = { INT_MIN, INT_MIN, INT_MIN };
-    bool flag = false;
-    float4 q1 = make_float4(0, 0, 0, 0), q2 = q1;
-    if (i < n) {
-        const float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
-        flag = (__float_as_uint(q3.w) & 1u) != 0;
-        pflag[i] = flag ? 1u : 0u;
-        if (q0.x == q0.x) { bmin[0] = bmax[0] = f2ord(q0.x); }
-        if (q0.y == q0.y) { bmin[1] = bmax[1] = f2ord(q0.y); }
-        if (q0.z == q0.z) { bmin[2] = bmax[2] = f2ord(q0.z); }
-        if (flag) { q1 = geo[4 * i + 1]; q2 = geo[4 * i + 2]; }
-    }
-    s_rad[tid] = 0.0f;
-    const unsigned bal = __ballot_sync(full, flag);
-    if (lane == 0) s_woff[warp + 1] = __popc(bal);
-    __syncthreads();
-    if (tid == 0) {
-        s_woff[0] = 0;
-        for (int w = 0; w < 8; ++w) s_woff[w + 1] += s_woff[w];
-    }
-    __syncthreads();
-    if (flag) {
-        const int slot = s_woff[warp] + __popc(bal & ((1u << lane) - 1u));
-        s_cov[slot][0] = q1.x; s_cov[slot][1] = q1.y; s_cov[slot][2] = q1.z;
-        s_cov[slot][3] = q1.w; s_cov[slot][4] = q2.x; s_cov[slot][5] = q2.y;
-        s_src[slot] = (uint16_t)tid;
-    }
-    __syncthreads();
-    const int npar = s_woff[8];
     unsigned int rbits = 0, rcount = 0;
     double rsum = 0.0;
-    if (tid < npar) {
-        const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
-        const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
-        if (rad > 0.0f && rad < FLT_MAX) { rbits = __float_as_uint(rad); rcount = 1; rsum = (double)rad; }
-        s_rad[s_src[tid]] = rad;
+    const int64_t ntiles = (n + 255) / 256;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i = tile * 256 + tid;
+        bool flag = false;
+        float4 q1 = make_float4(0, 0, 0, 0), q2 = q1;
+        if (i < n) {
+            const float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
+            flag = (__float_as_uint(q3.w) & 1u) != 0;
+            pflag[i] = flag ? 1u : 0u;
+            if (q0.x == q0.x) { const int o = f2ord(q0.x); bmin[0] = min(bmin[0], o); bmax[0] = max(bmax[0], o); }
+            if (q0.y == q0.y) { const int o = f2ord(q0.y); bmin[1] = min(bmin[1], o); bmax[1] = max(bmax[1], o); }
+            if (q0.z == q0.z) { const int o = f2ord(q0.z); bmin[2] = min(bmin[2], o); bmax[2] = max(bmax[2], o); }
+            if (flag) { q1 = geo[4 * i + 1]; q2 = geo[4 * i + 2]; }
+        }
+        s_rad[tid] = 0.0f;
+        const unsigned bal = __ballot_sync(full, flag);
+        if (lane == 0) s_woff[warp + 1] = __popc(bal);
+        __syncthreads();
+        if (tid == 0) {
+            s_woff[0] = 0;
+            for (int w = 0; w < 8; ++w) s_woff[w + 1] += s_woff[w];
+        }
+        __syncthreads();
+        if (flag) {
+            const int slot = s_woff[warp] + __popc(bal & ((1u << lane) - 1u));
+            s_cov[slot][0] = q1.x; s_cov[slot][1] = q1.y; s_cov[slot][2] = q1.z;
+            s_cov[slot][3] = q1.w; s_cov[slot][4] = q2.x; s_cov[slot][5] = q2.y;
+            s_src[slot] = (uint16_t)tid;
+        }
+        __syncthreads();
+        const int npar = s_woff[8];
+        if (tid < npar) {
+            const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
+            const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
+            if (rad > 0.0f && rad < FLT_MAX) { rbits = max(rbits, __float_as_uint(rad)); rcount += 1; rsum += (double)rad; }
+            s_rad[s_src[tid]] = rad;
+        }
+        __syncthreads();
+        if (i < n) radius[i] = s_rad[tid];
+        __syncthreads();
     }
-    __syncthreads();
-    if (i < n) radius[i] = s_rad[tid];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         bmin[a] = __reduce_min_sync(full, bmin[a]);
@@ -195,7 +185,17 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
     if (lane == 0) {
-#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_red[warp][a] = bmin[a]; s_red[warp][3 + a] = bmax[a]; }
+        s_red[warp][6] = (int)rbits; s_red[warp][7] = (int)rcount;
+        s_redd[warp] = rsum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            for (int a = 0; a < 3; ++a) { bmin[a] = min(bmin[a], s_red[w][a]); bmax[a] = max(bmax[a], s_red[w][3 + a]); }
+            rbits = max(rbits, (unsigned)s_red[w][6]); rcount += (unsigned)s_red[w][7];
+            rsum += s_redd[w];
+        }
         for (int a = 0; a < 3; ++a) {
             if (bmin[a] != INT_MAX) atomicMin(&stats->bbmin[a], bmin[a]);
             if (bmax[a] != INT_MIN) atomicMax(&stats->bbmax[a], bmax[a]);
@@ -558,7 +558,6 @@ struct MomArgs {
     int t_begin, t_end;           // this rank's slab of parents (cell order)
     int by_rank;                  // 1: row index = canonical rank (final place); 0: row index = t (staging for the exchange)
     float4* ogeo; float* osh;
-    uint64_t seed, rng_base; float pp;
     unsigned long long* counters;
 };
 
@@ -606,16 +605,9 @@ k_moments(MomArgs A)
             const float dm = fs(scaled, pmj);                        // mean - parent mean on lanes 0..2
             const float da = __shfl_sync(full, dm, sa), db = __shfl_sync(full, dm, sb);
             float outv = is_cov ? fs(scaled, fm(da, db)) : scaled;
-            Sym3 cv;
-            cv.e00 = __shfl_sync(full, outv, 4); cv.e01 = __shfl_sync(full, outv, 5); cv.e02 = __shfl_sync(full, outv, 6);
-            cv.e11 = __shfl_sync(full, outv, 7); cv.e12 = __shfl_sync(full, outv, 8); cv.e22 = __shfl_sync(full, outv, 9);
-            const float dt = det_sym3(cv);
             const uint32_t srank = __shfl_sync(full, pt.y, cur);
-            // pre-filter position of a merged parent = its rank; flag drawn there, mixture.cpp:257-259
-            const bool flag = parent_flag(A.seed, A.rng_base + (uint64_t)srank, A.pp);
             if (j == 3) outv = w_s;
-            if (j == 11) outv = dt;
-            if (j == 15) outv = __uint_as_float(flag ? 1u : 0u);
+            if (j == 11 || j == 15) outv = 0.0f;      // det and parent flag are filled in by k_finish
             const size_t orow_i = A.by_rank ? (size_t)srank : (size_t)(tb + cur);
             if (lane < 16) ogeof[16 * orow_i + lane] = outv;
             float* orow = A.osh + orow_i * Fp;
@@ -691,8 +683,7 @@ __global__ void k_orphan_flag(const float* __restrict__ sumlw, int64_t n, uint32
 __global__ void __launch_bounds__(256)
 k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, int64_t n,
           const uint32_t* __restrict__ oflag, const uint32_t* __restrict__ orank, uint32_t np,
-          float4* __restrict__ ogeo, float* __restrict__ osh,
-          uint64_t seed, uint64_t rng_base, float pp)
+          float4* __restrict__ ogeo, float* __restrict__ osh)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -709,7 +700,6 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
         const size_t dst = (size_t)np + __shfl_sync(full, myrank, src);
         float4 v;
         if (lane < 4) v = geo[4 * (size_t)ci + lane];
-        if (lane == 3) v.w = __uint_as_float(parent_flag(seed, rng_base + (uint64_t)dst, pp) ? 1u : 0u);
         if (lane < 4) ogeo[4 * dst + lane] = v;
         const float* srow = sh + (size_t)ci * Fp;
         float* drow = osh + dst * Fp;
@@ -718,18 +708,30 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
     }
 }
 
-// validity filter predicate on every pre-filter output row, mixture.cpp:262-270
-__global__ void k_validity(const float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
-                           const uint32_t* __restrict__ oflag, int64_t n_in, uint8_t* __restrict__ valid,
-                           unsigned long long* __restrict__ counters)
+// Per pre-filter output row j (merged parents [0,np) then orphans): determinant of the merged
+// covariance, fresh parent flag drawn at the pre-filter position (mixture.cpp:257-259) and the
+// validity predicate (mixture.cpp:262-270).  One THREAD per row: the Philox rounds and the
+// determinant used to run warp-uniformly once per parent inside the moment kernel.
+__global__ void k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
+                         const uint32_t* __restrict__ oflag, int64_t n_in, uint64_t seed, uint64_t rng_base,
+                         float pp, uint8_t* __restrict__ valid, unsigned long long* __restrict__ counters)
 {
     // pre-filter row count = parents + orphans, read on the device (the host learns it afterwards)
     const int64_t n = np + (int64_t)orank[n_in - 1] + (int64_t)oflag[n_in - 1];
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false;
     if (j < n) {
-        const float4 q0 = geo[4 * j];
-        const float dt = geo[4 * j + 2].w;
+        const float4 q0 = geo[4 * j], q1 = geo[4 * j + 1];
+        float4 q2 = geo[4 * j + 2];
+        float dt = q2.w;
+        if (j < np) {               // merged row: determinant in the reference's operation order
+            const Sym3 c = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
+            dt = det_sym3(c);
+            q2.w = dt;
+            geo[4 * j + 2] = q2;
+        }
+        reinterpret_cast<float*>(geo)[16 * j + 15] =
+            __uint_as_float(parent_flag(seed, rng_base + (uint64_t)j, pp) ? 1u : 0u);
         bad = (q0.x != q0.x || q0.y != q0.y || q0.z != q0.z) || (dt != dt) || dt <= 0.0f;
         valid[j] = bad ? 0 : 1;
     }
