@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhem_b200.so")
+LIB_PATH = os.environ.get("HEM_B200_LIB") or os.path.join(_HERE, "libhem_b200.so")   # override: kernel experiments only
 
 STEP_STATS_LEN = 18
 NCCL_ID_BYTES = 128

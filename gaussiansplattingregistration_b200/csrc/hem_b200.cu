@@ -76,10 +76,10 @@ struct hem_ctx {
     DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
     DevBuf radius, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
-    DevBuf pair_cnt, pair_off, pair_cnt_s, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, sumlw, oflag, orank;
-    DevBuf valid, vflag, vpos, cubtmp, counters, prep, nsel, tmp_geo, tmp_sh;
+    DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
+    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh;
     unsigned long long* h_counters = nullptr;   // pinned
-    PrepStats* h_prep = nullptr;                // pinned
+    Ctl* h_ctl = nullptr;                       // pinned
     cudaEvent_t ev[EV_COUNT] = {};
 
     // multi-GPU
@@ -265,35 +265,31 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     const float* sh = in.shp;
 
     // ---- S1 prep --------------------------------------------------------------------------
+    // control block + the arrays that must start from zero live in one allocation: one memset per step
+    //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) ]
+    const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
+    const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
+    const size_t ctl_bytes = off_sumlw + (size_t)n * 4;
+    CKR(ensure(ctx, ctx->ctlbuf, ctl_bytes));
+    Ctl* d_ctl = ctx->ctlbuf.as<Ctl>();
+    unsigned long long* d_counters = d_ctl->counters;
+    uint32_t* d_pair_cnt_s = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt_s);
+    uint32_t* d_pair_cnt = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt);
+    float* d_sumlw = (float*)((char*)ctx->ctlbuf.p + off_sumlw);
     CKR(ensure(ctx, ctx->radius, n * 4));
     CKR(ensure(ctx, ctx->pflag, n * 4));
     CKR(ensure(ctx, ctx->prank, n * 4));
-    CKR(ensure(ctx, ctx->prep, sizeof(PrepStats)));
-    CKR(ensure(ctx, ctx->counters, C_COUNT * sizeof(unsigned long long)));
-    {
-        PrepStats init;
-        for (int a = 0; a < 3; ++a) { init.bbmin[a] = INT_MAX; init.bbmax[a] = INT_MIN; }
-        init.max_radius_bits = 0; init.n_radius = 0; init.sum_radius = 0.0;
-        *ctx->h_prep = init;
-        CK(cudaMemcpyAsync(ctx->prep.p, ctx->h_prep, sizeof(PrepStats), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long), st));
-    }
-    k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(geo, n, distance_delta, ctx->radius.as<float>(),
-                                                ctx->pflag.as<uint32_t>(), ctx->prep.as<PrepStats>());
+    CK(cudaMemsetAsync(ctx->ctlbuf.p, 0, ctl_bytes, st));
+    k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
+        geo, n, distance_delta, ctx->radius.as<float>(), ctx->pflag.as<uint32_t>(), d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
     }));
-    // parent count = prank[n-1] + pflag[n-1]
-    uint32_t h_tail[2];
-    CK(cudaMemcpyAsync(ctx->h_prep, ctx->prep.p, sizeof(PrepStats), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->prank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ctx->h_counters[9], ctx->pflag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));                                      // sync A
-    memcpy(&h_tail[0], &ctx->h_counters[8], 4);
-    memcpy(&h_tail[1], &ctx->h_counters[9], 4);
-    const int64_t np = (int64_t)h_tail[0] + h_tail[1];
-    const PrepStats ps = *ctx->h_prep;
+    const Ctl ps = *ctx->h_ctl;
+    const int64_t np = (int64_t)ps.n_parents;
     S.n_parents = np;
     float max_radius = 0.0f;
     memcpy(&max_radius, &ps.max_radius_bits, 4);
@@ -306,8 +302,6 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CKR(ensure(ctx, out.sh, (size_t)cap_rows * std::max(Fp, 1) * 4));
     out.shp = out.sh.as<float>();
     CKR(ensure(ctx, ctx->valid, cap_rows));
-    CKR(ensure(ctx, ctx->sumlw, n * 4));
-    CK(cudaMemsetAsync(ctx->sumlw.p, 0, n * 4, st));
 
     int64_t P = 0;
     const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
@@ -317,8 +311,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         {
             float bmin[3], bmax[3];
             for (int a = 0; a < 3; ++a) {
-                bmin[a] = ps.bbmin[a] == INT_MAX ? 0.0f : ord2f(ps.bbmin[a]);
-                bmax[a] = ps.bbmax[a] == INT_MIN ? 0.0f : ord2f(ps.bbmax[a]);
+                bmin[a] = ps.bbmin_c[a] ? u2f(~ps.bbmin_c[a]) : 0.0f;
+                bmax[a] = ps.bbmax_u[a] ? u2f(ps.bbmax_u[a]) : 0.0f;
                 if (!std::isfinite(bmin[a])) bmin[a] = -FLT_MAX;
                 if (!std::isfinite(bmax[a])) bmax[a] = FLT_MAX;
             }
@@ -379,9 +373,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         std::vector<int64_t> tb(G + 1);
         for (int q = 0; q <= G; ++q) tb[q] = slab_bound(np, q, G);
         const int64_t my_np = tb[R + 1] - tb[R];
-        CKR(ensure(ctx, ctx->pair_cnt, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
-        CKR(ensure(ctx, ctx->pair_cnt_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->ptab, np * 8));
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
@@ -396,9 +388,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             const size_t chunk_cap = (size_t)my_np + pool_cap / (GATE_OUTCAP - 32) + 16;
             CKR(ensure(ctx, ctx->pool, pool_cap * 8));
             CKR(ensure(ctx, ctx->chunks, chunk_cap * 16));
-            CK(cudaMemsetAsync(ctx->pair_cnt_s.p, 0, (np + 1) * 4, st));
-            CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(unsigned long long), st));
-            CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_WORK, 0, sizeof(unsigned long long), st));
+            if (attempt > 0) {      // pool overflow retry: reopen the counters and the counts
+                CK(cudaMemsetAsync(d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
+                CK(cudaMemsetAsync(d_pair_cnt_s, 0, (size_t)(n + 1) * 4, st));
+                CK(cudaMemsetAsync(d_pair_cnt, 0, (size_t)(n + 1) * 4, st));
+            }
             GateArgs A;
             A.sp0 = ctx->sp0.as<float4>(); A.sp1 = ctx->sp1.as<float4>(); A.sp2 = ctx->sp2.as<float4>();
             A.sp3 = ctx->sp3.as<float4>(); A.cell_start = ctx->cell_start.as<uint32_t>();
@@ -406,24 +400,25 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.cthr = color_delta * color_delta * 0.5f;           // mixture.cpp:123
             A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
-            A.pair_cnt_s = ctx->pair_cnt_s.as<uint32_t>();
+            A.pair_cnt_s = d_pair_cnt_s;
+            A.pair_cnt = (G == 1) ? d_pair_cnt : nullptr;
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
             A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
-            A.counters = ctx->counters.as<unsigned long long>();
+            A.counters = d_counters;
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
             if (my_np > 0) {
-                k_gate<<<(unsigned)std::min<int64_t>(blocks_for(my_np, GATE_WARPS), (int64_t)ctx->sm_count * 4), GATE_WARPS * 32, 0, st>>>(A);
+                k_gate<<<(unsigned)std::min<int64_t>(blocks_for(my_np, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st>>>(A);
                 CK(cudaGetLastError());
                 ctx->n_launches++;
             }
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK1], st));
             if (G == 1) {       // single GPU: counts are complete, scan before the one host sync of this stage
                 CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
-                    return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt_s.as<uint32_t>(), ctx->pair_off_s.as<uint32_t>(),
+                    return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt_s, ctx->pair_off_s.as<uint32_t>(),
                                                          (int)(np + 1), st);
                 }));
             }
-            CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_counters, d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                              // sync B
             nchunks = ctx->h_counters[C_CHUNK];
             if (ctx->h_counters[C_POOL] <= pool_cap && nchunks <= chunk_cap) break;
@@ -435,9 +430,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             pb[1] = (int64_t)ctx->h_counters[C_POOL];
         } else {
             // exchange the per-parent counts, scan them everywhere, fetch the offsets at the slab bounds
-            CKR(allgather_ranges(ctx, ctx->pair_cnt_s.p, 4, tb.data()));
+            CKR(allgather_ranges(ctx, d_pair_cnt_s, 4, tb.data()));
             CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
-                return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt_s.as<uint32_t>(), ctx->pair_off_s.as<uint32_t>(),
+                return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt_s, ctx->pair_off_s.as<uint32_t>(),
                                                      (int)(np + 1), st);
             }));
             std::vector<uint32_t> hb(G + 1, 0);
@@ -458,12 +453,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
-        CK(cudaMemsetAsync(ctx->pair_cnt.p, 0, (np + 1) * 4, st));
-        k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_cnt_s.as<uint32_t>(), (int)np,
-                                                          ctx->pair_cnt.as<uint32_t>());
-        CK(cudaGetLastError()); ctx->n_launches++;
+        if (G > 1) {        // sharded: counts arrive in cell order, put them in canonical order here
+            k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), d_pair_cnt_s, (int)np, d_pair_cnt);
+            CK(cudaGetLastError()); ctx->n_launches++;
+        }
         CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
-            return cub::DeviceScan::ExclusiveSum(tt, bb, ctx->pair_cnt.as<uint32_t>(), ctx->pair_off.as<uint32_t>(),
+            return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt, ctx->pair_off.as<uint32_t>(),
                                                  (int)(np + 1), st);
         }));
         if (P > 0) {
@@ -484,7 +479,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                        ctx->csr_wl.as<float>(), ctx->sv.as<float>(), (int)P, 0, cbits, st);
             }));
             k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P,
-                                                          ctx->sumlw.as<float>());
+                                                          d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
@@ -492,9 +487,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         // ---- S4 moments -------------------------------------------------------------------------------
         MomArgs M;
         M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = ctx->ptab.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
-        M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = ctx->sumlw.as<float>();
+        M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = d_sumlw;
         M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
-        M.counters = ctx->counters.as<unsigned long long>();
+        M.counters = d_counters;
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
@@ -502,7 +497,6 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->stage_sh, (size_t)np * std::max(Fp, 1) * 4));
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
-        CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_WORK, 0, sizeof(unsigned long long), st));
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
             k_moments<<<(unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st>>>(M);
@@ -528,31 +522,22 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
 
     // ---- S5 orphans + filter ---------------------------------------------------------------------------
-    CKR(ensure(ctx, ctx->oflag, n * 4));
     CKR(ensure(ctx, ctx->orank, n * 4));
-    k_orphan_flag<<<blocks_for(n, 256), 256, 0, st>>>(ctx->sumlw.as<float>(), n, ctx->oflag.as<uint32_t>());
-    CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
-        return cub::DeviceScan::ExclusiveSum(t, b, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(), (int)n, st);
+        cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
+        return cub::DeviceScan::ExclusiveSum(t, b, it, ctx->orank.as<uint32_t>(), (int)n, st);
     }));
-    k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, ctx->oflag.as<uint32_t>(), ctx->orank.as<uint32_t>(),
+    k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
                                                    (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
     CK(cudaGetLastError()); ctx->n_launches++;
     // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
-    CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + C_INVALID, 0, sizeof(unsigned long long), st));
-    k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(),
-                                                         ctx->oflag.as<uint32_t>(), n, ctx->seed, rng_base, pp,
-                                                         ctx->valid.as<uint8_t>(), ctx->counters.as<unsigned long long>());
+    k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
+                                                         ctx->seed, rng_base, pp, ctx->valid.as<uint8_t>(), d_counters);
     CK(cudaGetLastError()); ctx->n_launches++;
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ctx->h_counters[8], ctx->orank.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ctx->h_counters[9], ctx->oflag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_counters, d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));                                      // sync C
-    uint32_t ot[2];
-    memcpy(&ot[0], &ctx->h_counters[8], 4);
-    memcpy(&ot[1], &ctx->h_counters[9], 4);
-    const int64_t norph = (int64_t)ot[0] + ot[1];
+    const int64_t norph = (int64_t)ctx->h_counters[C_NORPH];
     const int64_t npre = np + norph;
     const int64_t ninvalid = (int64_t)ctx->h_counters[C_INVALID];
     S.n_orphans = norph;
@@ -600,7 +585,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         StepPairs& K = ctx->pairs[l];
         K = StepPairs();
         K.sumlw.resize(n);
-        CK(cudaMemcpyAsync(K.sumlw.data(), ctx->sumlw.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(K.sumlw.data(), d_sumlw, n * 4, cudaMemcpyDeviceToHost, st));
         std::vector<uint32_t> pflag(n);
         std::vector<float> rad(n);
         CK(cudaMemcpyAsync(pflag.data(), ctx->pflag.p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -658,7 +643,7 @@ hem_ctx* hem_create(int device, uint64_t seed)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_prep, sizeof(PrepStats)) != cudaSuccess) {
+        cudaMallocHost((void**)&ctx->h_ctl, sizeof(Ctl)) != cudaSuccess) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
         return nullptr;
@@ -679,12 +664,12 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
-                      &ctx->pair_cnt, &ctx->pair_off, &ctx->pair_cnt_s, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
-                      &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->sumlw, &ctx->oflag, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->counters, &ctx->prep, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh };
+                      &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
+                      &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh };
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    if (ctx->h_prep) cudaFreeHost(ctx->h_prep);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -38,15 +38,20 @@ struct GridP {
     int gx, gy, gz;
 };
 
-// device counters (unsigned long long each)
-enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_NPAR = 4, C_WORK = 5, C_COUNT = 8 };
+// Per-step control block.  Everything in it (and the per-parent / per-child arrays that follow
+// it in the same allocation) starts from zero, so ONE memset opens a step.
+enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_WORK = 4, C_WORK2 = 5, C_COUNT = 8 };
 
-// statistics block written by k_prep
-struct PrepStats {
-    int bbmin[3];          // ordered-int encoded floats
-    int bbmax[3];
-    unsigned int max_radius_bits;
-    unsigned int n_radius;        // parents with finite positive radius
+struct Ctl {
+    unsigned long long counters[C_COUNT];
+    // bounding box of the means in a zero-initialisable encoding: u(x) = ord(x) ^ 0x80000000 is
+    // monotone in x as an unsigned; bbmax_u = max u(x), bbmin_c = max ~u(x); 0 means "no finite mean"
+    unsigned int bbmax_u[3];
+    unsigned int bbmin_c[3];
+    unsigned int max_radius_bits;   // positive floats order like their bit patterns
+    unsigned int n_radius;          // parents with finite positive radius
+    unsigned int n_parents;
+    unsigned int pad_;
     double sum_radius;
 };
 
@@ -55,8 +60,10 @@ __device__ __forceinline__ int f2ord(float f)
     int i = __float_as_int(f);
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
-__host__ __device__ __forceinline__ float ord2f(int i)
+__device__ __forceinline__ unsigned int f2u(float f) { return (unsigned int)f2ord(f) ^ 0x80000000u; }
+__host__ __device__ __forceinline__ float u2f(unsigned int u)
 {
+    int i = (int)(u ^ 0x80000000u);
     int b = i >= 0 ? i : i ^ 0x7fffffff;
 #ifdef __CUDA_ARCH__
     return __int_as_float(b);
@@ -116,7 +123,7 @@ __global__ void k_export(const float4* __restrict__ geo, int64_t n, float* __res
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* __restrict__ radius,
-       uint32_t* __restrict__ pflag, PrepStats* __restrict__ stats)
+       uint32_t* __restrict__ pflag, Ctl* __restrict__ ctl)
 {
     // * The FP64 closed-form eigenvalue is ~400 instructions and only one component in
     //   hemReduction is a parent: the parents of a 256-component tile are compacted through
@@ -131,8 +138,8 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     __shared__ double s_redd[8];
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int bmin[3] = { INT_MAX, INT_MAX, INT_MAX }, bmax[3] = { INT_MIN, INT_MIN, INT_MIN };
-    unsigned int rbits = 0, rcount = 0;
+    unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
+    unsigned int rbits = 0, rcount = 0, pcount = 0;
     double rsum = 0.0;
     const int64_t ntiles = (n + 255) / 256;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -143,9 +150,9 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
             const float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
             flag = (__float_as_uint(q3.w) & 1u) != 0;
             pflag[i] = flag ? 1u : 0u;
-            if (q0.x == q0.x) { const int o = f2ord(q0.x); bmin[0] = min(bmin[0], o); bmax[0] = max(bmax[0], o); }
-            if (q0.y == q0.y) { const int o = f2ord(q0.y); bmin[1] = min(bmin[1], o); bmax[1] = max(bmax[1], o); }
-            if (q0.z == q0.z) { const int o = f2ord(q0.z); bmin[2] = min(bmin[2], o); bmax[2] = max(bmax[2], o); }
+            if (q0.x == q0.x) { const unsigned o = f2u(q0.x); bmax[0] = max(bmax[0], o); bminc[0] = max(bminc[0], ~o); }
+            if (q0.y == q0.y) { const unsigned o = f2u(q0.y); bmax[1] = max(bmax[1], o); bminc[1] = max(bminc[1], ~o); }
+            if (q0.z == q0.z) { const unsigned o = f2u(q0.z); bmax[2] = max(bmax[2], o); bminc[2] = max(bminc[2], ~o); }
             if (flag) { q1 = geo[4 * i + 1]; q2 = geo[4 * i + 2]; }
         }
         s_rad[tid] = 0.0f;
@@ -165,6 +172,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
         }
         __syncthreads();
         const int npar = s_woff[8];
+        if (tid == 0) pcount += (unsigned)npar;
         if (tid < npar) {
             const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
             const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
@@ -177,33 +185,34 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        bmin[a] = __reduce_min_sync(full, bmin[a]);
         bmax[a] = __reduce_max_sync(full, bmax[a]);
+        bminc[a] = __reduce_max_sync(full, bminc[a]);
     }
     rbits = __reduce_max_sync(full, rbits);
     rcount = __reduce_add_sync(full, rcount);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
     if (lane == 0) {
-        for (int a = 0; a < 3; ++a) { s_red[warp][a] = bmin[a]; s_red[warp][3 + a] = bmax[a]; }
+        for (int a = 0; a < 3; ++a) { s_red[warp][a] = (int)bminc[a]; s_red[warp][3 + a] = (int)bmax[a]; }
         s_red[warp][6] = (int)rbits; s_red[warp][7] = (int)rcount;
         s_redd[warp] = rsum;
     }
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < 8; ++w) {
-            for (int a = 0; a < 3; ++a) { bmin[a] = min(bmin[a], s_red[w][a]); bmax[a] = max(bmax[a], s_red[w][3 + a]); }
+            for (int a = 0; a < 3; ++a) { bminc[a] = max(bminc[a], (unsigned)s_red[w][a]); bmax[a] = max(bmax[a], (unsigned)s_red[w][3 + a]); }
             rbits = max(rbits, (unsigned)s_red[w][6]); rcount += (unsigned)s_red[w][7];
             rsum += s_redd[w];
         }
         for (int a = 0; a < 3; ++a) {
-            if (bmin[a] != INT_MAX) atomicMin(&stats->bbmin[a], bmin[a]);
-            if (bmax[a] != INT_MIN) atomicMax(&stats->bbmax[a], bmax[a]);
+            if (bmax[a]) atomicMax(&ctl->bbmax_u[a], bmax[a]);
+            if (bminc[a]) atomicMax(&ctl->bbmin_c[a], bminc[a]);
         }
+        if (pcount) atomicAdd(&ctl->n_parents, pcount);
         if (rcount) {
-            atomicMax(&stats->max_radius_bits, rbits);
-            atomicAdd(&stats->n_radius, rcount);
-            atomicAdd(&stats->sum_radius, rsum);
+            atomicMax(&ctl->max_radius_bits, rbits);
+            atomicAdd(&ctl->n_radius, rcount);
+            atomicAdd(&ctl->sum_radius, rsum);
         }
     }
 }
@@ -253,6 +262,9 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
 // S3: gates + likelihood.  One warp per parent, parents taken in cell order so
 // that neighbouring warps stream the same cell runs out of L2.
 // ---------------------------------------------------------------------------
+#ifndef HEM_GATE_MINBLOCKS
+#define HEM_GATE_MINBLOCKS 4
+#endif
 constexpr int GATE_WARPS = 8;
 constexpr int GATE_OUTCAP = 128;
 
@@ -269,6 +281,7 @@ struct GateArgs {
     int t_begin, t_end;          // this rank's slab of parents (cell order)
     float cthr, kthr, decay2;
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
+    uint32_t* pair_cnt;          // [np+1] same, indexed by canonical rank (single GPU; NULL when sharded)
     uint2* pool; unsigned long long pool_cap;
     uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count, prefix inside the parent)
     unsigned long long* counters;
@@ -292,7 +305,7 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
     o[4] = make_float4(radius[s], geo[4 * (size_t)s].w, __uint_as_float(srank), __uint_as_float(s));
 }
 
-__global__ void __launch_bounds__(GATE_WARPS * 32, 4)
+__global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
 k_gate(GateArgs A)
 {
     __shared__ uint32_t s_q[GATE_WARPS][64];
@@ -363,11 +376,11 @@ k_gate(GateArgs A)
             uint32_t jj = 0;
             if (lane < m) {
                 jj = q[lane];
-                const float4 c1 = A.sp1[jj];
+                // all four planes are requested at once (the colour gate rejects only ~1 in 5)
+                const float4 c1 = A.sp1[jj], c0 = A.sp0[jj], c2 = A.sp2[jj], c3 = A.sp3[jj];
                 // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
                 const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
                 if (!(cdist > A.cthr)) {
-                    const float4 c0 = A.sp0[jj], c2 = A.sp2[jj], c3 = A.sp3[jj];
                     // KLD(child || parent), gaussian.hpp:106-109
                     const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
                     const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
@@ -439,9 +452,9 @@ k_gate(GateArgs A)
                 const uint32_t total = __shfl_sync(full, incl, 31);
                 const uint32_t excl = incl - len;
 
-                // lanes walk the concatenation of the runs, 32 candidates per iteration
-                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                    const uint32_t tt = t0 + lane;
+                // lanes walk the concatenation of the runs, 32 candidates per iteration; the slot and
+                // the position of the NEXT window are fetched before the current one is tested
+                auto locate = [&](uint32_t tt) -> uint32_t {
                     int row = 0;
 #pragma unroll
                     for (int step = 16; step > 0; step >>= 1) {
@@ -449,10 +462,21 @@ k_gate(GateArgs A)
                         if (v <= tt) row += step;
                     }
                     row = min(row, 31);
-                    const uint32_t jj = __shfl_sync(full, ra, row) + (tt - __shfl_sync(full, excl, row));
+                    return __shfl_sync(full, ra, row) + (tt - __shfl_sync(full, excl, row));
+                };
+                uint32_t jn = locate((uint32_t)lane);
+                float4 cn = make_float4(0, 0, 0, 0);
+                if ((uint32_t)lane < total) cn = A.sp0[jn];
+                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                    const uint32_t tt = t0 + lane;
+                    const uint32_t jj = jn;
+                    const float4 c0 = cn;
+                    if (t0 + 32 < total) {                      // uniform
+                        jn = locate(tt + 32);
+                        if (tt + 32 < total) cn = A.sp0[jn];
+                    }
                     bool in = false;
                     if (tt < total) {
-                        const float4 c0 = A.sp0[jj];
                         const uint32_t w = __float_as_uint(c0.w);
                         // radius test, pointindex.cpp:138 (query - point); parent exclusion, mixture.cpp:131-133
                         const float d2 = sqdist3(p0.x, p0.y, p0.z, c0.x, c0.y, c0.z);
@@ -475,7 +499,10 @@ k_gate(GateArgs A)
             if (qn > 0) process(qn);
             flush();
         }
-        if (lane == 0) A.pair_cnt_s[t] = total_out;
+        if (lane == 0) {
+            A.pair_cnt_s[t] = total_out;
+            if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z)] = total_out;
+        }
         __syncwarp();
     }
 }
@@ -578,7 +605,7 @@ k_moments(MomArgs A)
 
     for (;;) {
         unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
+        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK2], 1ull);
         const int tb = A.t_begin + (int)__shfl_sync(full, ticket, 0) * MOM_B;
         if (tb >= A.t_end) break;
         const int nb = min(MOM_B, A.t_end - tb);
@@ -657,10 +684,12 @@ k_moments(MomArgs A)
                         while (k0 + g + u == nextb && cur < nb - 1) advance();   // parent boundary (empty parents too)
                         const float dv = fs(gv[u], pmj);
                         const float da = __shfl_sync(full, dv, sa), db = __shfl_sync(full, dv, sb);
-                        const float val = (j == 3) ? 1.0f : (is_cov ? fa(gv[u], fm(da, db)) : gv[u]);
-                        accg = fa(accg, fm(wc[u], val));
-                        sh0 = fa(sh0, fm(v0[u], wc[u]));
-                        sh1 = fa(sh1, fm(v1[u], wc[u]));
+                        // tolerance-class sums (the reference's own summation order is not reproducible,
+                        // DESIGN.md §2): fused multiply-adds
+                        const float val = (j == 3) ? 1.0f : (is_cov ? fmaf(da, db, gv[u]) : gv[u]);
+                        accg = fmaf(wc[u], val, accg);
+                        sh0 = fmaf(v0[u], wc[u], sh0);
+                        sh1 = fmaf(v1[u], wc[u], sh1);
                     }
                 }
             }
@@ -674,15 +703,14 @@ k_moments(MomArgs A)
 // ---------------------------------------------------------------------------
 // S5: orphans (mixture.cpp:251-253), their flags (:257-259) and validity (:262-282)
 // ---------------------------------------------------------------------------
-__global__ void k_orphan_flag(const float* __restrict__ sumlw, int64_t n, uint32_t* __restrict__ oflag)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) oflag[i] = sumlw[i] == 0.0f ? 1u : 0u;
-}
+// orphan predicate, mixture.cpp:251-253: claimed by no parent <=> sumLw stayed exactly 0
+struct IsOrphan {
+    __host__ __device__ __forceinline__ uint32_t operator()(const float& v) const { return v == 0.0f ? 1u : 0u; }
+};
 
 __global__ void __launch_bounds__(256)
 k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, int64_t n,
-          const uint32_t* __restrict__ oflag, const uint32_t* __restrict__ orank, uint32_t np,
+          const float* __restrict__ sumlw, const uint32_t* __restrict__ orank, uint32_t np,
           float4* __restrict__ ogeo, float* __restrict__ osh)
 {
     const unsigned full = 0xffffffffu;
@@ -690,7 +718,7 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
     const int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (wbase >= n) return;
     const int64_t i = wbase + lane;
-    const bool orphan = i < n && oflag[i] != 0;
+    const bool orphan = i < n && sumlw[i] == 0.0f;
     unsigned m = __ballot_sync(full, orphan);
     const uint32_t myrank = orphan ? orank[i] : 0u;
     while (m) {
@@ -713,12 +741,14 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
 // validity predicate (mixture.cpp:262-270).  One THREAD per row: the Philox rounds and the
 // determinant used to run warp-uniformly once per parent inside the moment kernel.
 __global__ void k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
-                         const uint32_t* __restrict__ oflag, int64_t n_in, uint64_t seed, uint64_t rng_base,
+                         const float* __restrict__ sumlw, int64_t n_in, uint64_t seed, uint64_t rng_base,
                          float pp, uint8_t* __restrict__ valid, unsigned long long* __restrict__ counters)
 {
     // pre-filter row count = parents + orphans, read on the device (the host learns it afterwards)
-    const int64_t n = np + (int64_t)orank[n_in - 1] + (int64_t)oflag[n_in - 1];
+    const int64_t norph = (int64_t)orank[n_in - 1] + (sumlw[n_in - 1] == 0.0f ? 1 : 0);
+    const int64_t n = np + norph;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) counters[C_NORPH] = (unsigned long long)norph;
     bool bad = false;
     if (j < n) {
         const float4 q0 = geo[4 * j], q1 = geo[4 * j + 1];
