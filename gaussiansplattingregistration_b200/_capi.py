@@ -36,6 +36,8 @@ SIGNATURES = {
     "hem_level_size": (C.c_int64, [C.c_void_p, C.c_int]),
     "hem_level_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hem_bind_output": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "hem_clear_outputs": (C.c_int, [C.c_void_p]),
     "hem_step_stats": (C.c_int, [C.c_void_p, C.c_int, _d]),
     "hem_get_info": (C.c_int, [C.c_void_p, C.c_char_p, _d]),
     "hem_step_pairs": (C.c_int, [C.c_void_p, C.c_int, _u32, _i64, _u32, _f, _f, _f]),

@@ -82,6 +82,13 @@ struct hem_ctx {
     Ctl* h_ctl = nullptr;                       // pinned
     cudaEvent_t ev[EV_COUNT] = {};
 
+    // copy/compute overlap: SH rows arrive and finished levels leave on a second stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_geo = nullptr, ev_sh = nullptr, ev_level = nullptr;
+    bool sh_pending = false;                     // level-0 SH H2D still in flight on copy_stream
+    struct OutBind { float *xyz = nullptr, *color = nullptr, *opacity = nullptr, *cov6 = nullptr, *sh = nullptr; int64_t cap = 0; bool set = false; };
+    std::vector<OutBind> binds;
+
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -497,6 +504,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->stage_sh, (size_t)np * std::max(Fp, 1) * 4));
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
+        if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
             k_moments<<<(unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st>>>(M);
@@ -522,6 +530,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
 
     // ---- S5 orphans + filter ---------------------------------------------------------------------------
+    if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
     CKR(ensure(ctx, ctx->orank, n * 4));
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
@@ -608,6 +617,54 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     return HEM_OK;
 }
 
+int from_device(hem_ctx* ctx, void* dst, size_t bytes, DevBuf& stage, void** dev_out, bool* staged)
+{
+    *staged = false;
+    if (!dst) { *dev_out = nullptr; return HEM_OK; }
+    if (is_device_ptr(dst)) { *dev_out = dst; return HEM_OK; }
+    CKR(ensure(ctx, stage, bytes));
+    *dev_out = stage.p;
+    *staged = true;
+    return HEM_OK;
+}
+
+// one level out in the reference's array layout, enqueued on `st` (no synchronisation here)
+int export_level(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
+                 float* weight, uint8_t* is_parent, cudaStream_t st)
+{
+    Level& L = ctx->levels[level];
+    const int64_t n = L.n;
+    if (n == 0) return HEM_OK;
+    const int F = ctx->F;
+    void *dx, *dc, *dop, *dcv, *dw, *df;
+    bool sx, sc, sop, scv, sw, sf;
+    CKR(from_device(ctx, xyz, (size_t)n * 12, ctx->out_a, &dx, &sx));
+    CKR(from_device(ctx, color, (size_t)n * 12, ctx->out_b, &dc, &sc));
+    CKR(from_device(ctx, opacity, (size_t)n * 4, ctx->out_c, &dop, &sop));
+    CKR(from_device(ctx, cov6, (size_t)n * 24, ctx->out_d, &dcv, &scv));
+    CKR(from_device(ctx, weight, (size_t)n * 4, ctx->out_f, &dw, &sw));
+    CKR(from_device(ctx, is_parent, (size_t)n, ctx->out_g, &df, &sf));
+    if (sh && F > 0) {       // rows are stored in the caller's layout: plain DMA (D2H or D2D), issued first (largest)
+        const bool to_dev = is_device_ptr(sh);
+        CK(cudaMemcpyAsync(sh, L.shp, (size_t)n * F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (!to_dev) ctx->bytes_d2h += (size_t)n * F * 4;
+    }
+    if (dx || dc || dop || dcv || dw || df) {
+        k_export<<<blocks_for(n, 256), 256, 0, st>>>(L.geo.as<float4>(), n, (float*)dx, (float*)dc, (float*)dop, (float*)dcv,
+                                                      (float*)dw, (uint8_t*)df);
+        CK(cudaGetLastError()); ctx->n_launches++;
+    }
+    if (sx) CK(cudaMemcpyAsync(xyz, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    if (sc) CK(cudaMemcpyAsync(color, dc, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    if (sop) CK(cudaMemcpyAsync(opacity, dop, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (scv) CK(cudaMemcpyAsync(cov6, dcv, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    if (sw) CK(cudaMemcpyAsync(weight, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (sf) CK(cudaMemcpyAsync(is_parent, df, (size_t)n, cudaMemcpyDeviceToHost, st));
+    ctx->bytes_d2h += (sx ? (size_t)n * 12 : 0) + (sc ? (size_t)n * 12 : 0) + (sop ? (size_t)n * 4 : 0) +
+                      (scv ? (size_t)n * 24 : 0) + (sw ? (size_t)n * 4 : 0) + (sf ? (size_t)n : 0);
+    return HEM_OK;
+}
+
 } // namespace
 
 // ===========================================================================
@@ -649,6 +706,10 @@ hem_ctx* hem_create(int device, uint64_t seed)
         return nullptr;
     }
     ctx->stream = ctx->own_stream;
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_sh, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_level, cudaEventDisableTiming);
     if (const char* cs = getenv("HEM_CELL_SCALE")) { double v = atof(cs); if (v > 0) ctx->cell_scale = v; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
@@ -671,6 +732,8 @@ void hem_destroy(hem_ctx* ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (cudaEvent_t e : { ctx->ev_geo, ctx->ev_sh, ctx->ev_level }) if (e) cudaEventDestroy(e);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -740,17 +803,36 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
             CKR(ensure(ctx, L0.sh, (size_t)n * std::max(Fp, 1) * 4));
             L0.shp = L0.sh.as<float>();
             if (Fp > 0) {
-                CK(cudaMemcpyAsync(L0.sh.p, sh, (size_t)n * Fp * 4, cudaMemcpyHostToDevice, st));
+                // the SH rows (3/4 of the bytes) are first read by the level-0 moment kernel: their H2D
+                // runs on the copy stream, behind the geometry, under the prep / grid / gate kernels
+                CK(cudaEventRecord(ctx->ev_geo, st));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_geo, 0));
+                CK(cudaMemcpyAsync(L0.sh.p, sh, (size_t)n * Fp * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaEventRecord(ctx->ev_sh, ctx->copy_stream));
+                ctx->sh_pending = true;
                 ctx->bytes_h2d += (size_t)n * Fp * 4;
             }
         }
     }
     uint64_t base = ctx->rng_base_set ? ctx->rng_base : (uint64_t)n;
+    bool bind_too_small = false;
     for (uint32_t l = 0; l < cluster_level; ++l) {
         CKR(run_step(ctx, (int)l, hem_reduction, distance_delta, color_delta, decay_rate, base));
         base += (uint64_t)(ctx->stats[l].n_parents + ctx->stats[l].n_orphans);    // pre-filter size, mixture.cpp:257-259
+        // a bound output leaves on the copy stream while the next level is being built
+        const size_t lv = (size_t)l + 1;
+        if (lv < ctx->binds.size() && ctx->binds[lv].set) {
+            const hem_ctx::OutBind& B = ctx->binds[lv];
+            if (B.cap < ctx->levels[lv].n) { bind_too_small = true; continue; }
+            CK(cudaEventRecord(ctx->ev_level, st));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_level, 0));
+            CKR(export_level(ctx, (int)lv, B.xyz, B.color, B.opacity, B.cov6, B.sh, nullptr, nullptr, ctx->copy_stream));
+        }
     }
+    if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }
     return HEM_OK;
 }
 
@@ -762,53 +844,32 @@ int64_t hem_level_size(const hem_ctx* ctx, int level)
     return ctx->levels[level].n;
 }
 
-static int from_device(hem_ctx* ctx, void* dst, size_t bytes, DevBuf& stage, void** dev_out, bool* staged)
-{
-    *staged = false;
-    if (!dst) { *dev_out = nullptr; return HEM_OK; }
-    if (is_device_ptr(dst)) { *dev_out = dst; return HEM_OK; }
-    CKR(ensure(ctx, stage, bytes));
-    *dev_out = stage.p;
-    *staged = true;
-    return HEM_OK;
-}
-
 int hem_level_copy(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
                    float* weight, uint8_t* is_parent)
 {
     if (!ctx) return HEM_ERR_INVALID;
     if (level < 0 || level > (int)ctx->stats.size() || (size_t)level >= ctx->levels.size()) { ctx->err = "level not built"; return HEM_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    Level& L = ctx->levels[level];
-    const int64_t n = L.n;
-    if (n == 0) return HEM_OK;
-    const int F = ctx->F;
-    void *dx, *dc, *dop, *dcv, *dw, *df;
-    bool sx, sc, sop, scv, sw, sf;
-    CKR(from_device(ctx, xyz, (size_t)n * 12, ctx->out_a, &dx, &sx));
-    CKR(from_device(ctx, color, (size_t)n * 12, ctx->out_b, &dc, &sc));
-    CKR(from_device(ctx, opacity, (size_t)n * 4, ctx->out_c, &dop, &sop));
-    CKR(from_device(ctx, cov6, (size_t)n * 24, ctx->out_d, &dcv, &scv));
-    CKR(from_device(ctx, weight, (size_t)n * 4, ctx->out_f, &dw, &sw));
-    CKR(from_device(ctx, is_parent, (size_t)n, ctx->out_g, &df, &sf));
-    k_export<<<blocks_for(n, 256), 256, 0, st>>>(L.geo.as<float4>(), n, (float*)dx, (float*)dc, (float*)dop, (float*)dcv,
-                                                  (float*)dw, (uint8_t*)df);
-    CK(cudaGetLastError()); ctx->n_launches++;
-    if (sh && F > 0) {       // rows are stored in the caller's layout: plain DMA (D2H or D2D)
-        const bool to_dev = is_device_ptr(sh);
-        CK(cudaMemcpyAsync(sh, L.shp, (size_t)n * F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        if (!to_dev) ctx->bytes_d2h += (size_t)n * F * 4;
-    }
-    if (sx) CK(cudaMemcpyAsync(xyz, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
-    if (sc) CK(cudaMemcpyAsync(color, dc, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
-    if (sop) CK(cudaMemcpyAsync(opacity, dop, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (scv) CK(cudaMemcpyAsync(cov6, dcv, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-    if (sw) CK(cudaMemcpyAsync(weight, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (sf) CK(cudaMemcpyAsync(is_parent, df, (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    ctx->bytes_d2h += (sx ? (size_t)n * 12 : 0) + (sc ? (size_t)n * 12 : 0) + (sop ? (size_t)n * 4 : 0) +
-                      (scv ? (size_t)n * 24 : 0) + (sw ? (size_t)n * 4 : 0) + (sf ? (size_t)n : 0);
+    CKR(export_level(ctx, level, xyz, color, opacity, cov6, sh, weight, is_parent, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HEM_OK;
+}
+
+int hem_bind_output(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
+                    int64_t capacity_rows)
+{
+    if (!ctx || level < 1 || level > 64 || capacity_rows < 0) return HEM_ERR_INVALID;
+    if (ctx->binds.size() <= (size_t)level) ctx->binds.resize((size_t)level + 1);
+    hem_ctx::OutBind& B = ctx->binds[level];
+    B.xyz = xyz; B.color = color; B.opacity = opacity; B.cov6 = cov6; B.sh = sh; B.cap = capacity_rows;
+    B.set = xyz || color || opacity || cov6 || sh;
+    return HEM_OK;
+}
+
+int hem_clear_outputs(hem_ctx* ctx)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    ctx->binds.clear();
     return HEM_OK;
 }
 

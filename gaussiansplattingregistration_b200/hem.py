@@ -158,6 +158,29 @@ class HemContext:
                                                 float(distance_delta), float(color_delta), float(decay_rate), pm))
         return self.num_levels
 
+    def bind_output(self, level: int, xyz=None, colors=None, opacity=None, cov6=None, sh=None):
+        """Bind caller-owned destination buffers (numpy views of pinned memory, or torch
+        tensors) for `level`; the next ``build`` copies the level out on a second stream as
+        soon as it is complete (``hem_bind_output``).  Row capacity = rows of the smallest buffer."""
+        bufs = [b for b in (xyz, colors, opacity, cov6, sh) if b is not None]
+        cap = min(int(b.shape[0]) for b in bufs) if bufs else 0
+        ptrs = []
+        for a in (xyz, colors, opacity, cov6, sh):
+            if a is None:
+                ptrs.append(None)
+            elif _is_torch(a):
+                ptrs.append(C.c_void_p(a.data_ptr()))
+            else:
+                assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float32
+                ptrs.append(C.c_void_p(a.ctypes.data))
+        self._bound = getattr(self, "_bound", {})
+        self._bound[level] = (xyz, colors, opacity, cov6, sh)          # keep alive
+        self._check(self._lib.hem_bind_output(self._h, int(level), *ptrs, cap))
+
+    def clear_outputs(self):
+        self._bound = {}
+        self._check(self._lib.hem_clear_outputs(self._h))
+
     @property
     def num_levels(self) -> int:
         return int(self._lib.hem_num_levels(self._h))

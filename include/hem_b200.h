@@ -102,6 +102,16 @@ int hem_level_copy(hem_ctx* ctx, int level,
                    float* xyz, float* color, float* opacity, float* cov6, float* sh,
                    float* weight, uint8_t* is_parent);
 
+/* Optional copy/compute overlap for host callers: bind destination buffers (ideally pinned)
+ * for level `level` (1..cluster_level) BEFORE hem_build_pyramid; the level is then copied out
+ * on a second stream as soon as it is complete, while the next level is being built, and the
+ * build returns with the data in place.  capacity_rows must be >= the level's size (n is always
+ * enough); any pointer may be NULL.  Bindings persist until hem_clear_outputs.  (A host `sh`
+ * INPUT is likewise uploaded on the second stream, under the level-0 grid and gate kernels.) */
+int hem_bind_output(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
+                    int64_t capacity_rows);
+int hem_clear_outputs(hem_ctx* ctx);
+
 /* Per-step statistics of clustering step `step` (input = level `step`).
  * out[0..15]:
  *   0 n_in  1 n_parents  2 n_pairs  3 n_orphans  4 n_dropped  5 n_out

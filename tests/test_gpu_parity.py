@@ -223,3 +223,31 @@ def test_gpu_mixture_bind_drop_in():
                    opacity=np.asarray(opac, np.float32), cov6=np.asarray(cov, np.float32), sh=np.asarray(feats, np.float32))
         want = {k: v for k, v in r.level(l).items() if k in got}
         assert_level_close(got, want, what=f"mixture_bind level {l}")
+
+
+def test_gpu_bound_outputs_and_host_upload_overlap(hemctx):
+    """hem_bind_output: levels copied out on the copy stream during the build must equal a
+    plain readback; host SH input goes up on the copy stream (same results as device input)."""
+    import torch
+    c = synth(80000, seed=29, density=5000.0)
+    hemctx.build(*c.arrays(), cluster_level=3)
+    want = [hemctx.level(l) for l in range(4)]
+    bufs = {}
+    for l in (1, 2, 3):
+        cap = c.n
+        bufs[l] = [torch.empty((cap, 3)).pin_memory().numpy(), torch.empty((cap, 3)).pin_memory().numpy(),
+                   torch.empty(cap).pin_memory().numpy(), torch.empty((cap, 6)).pin_memory().numpy(),
+                   torch.empty((cap, 45)).pin_memory().numpy()]
+        hemctx.bind_output(l, *bufs[l])
+    hemctx.build(*c.arrays(), cluster_level=3)
+    for l in (1, 2, 3):
+        m = hemctx.level_size(l)
+        for k, b in zip(("xyz", "colors", "opacity", "cov6", "sh"), bufs[l]):
+            assert np.array_equal(b[:m], want[l][k]), f"bound output differs: level {l} {k}"
+    # a too-small binding is reported, the level stays retrievable
+    from gaussiansplattingregistration_b200._capi import HemError
+    hemctx.bind_output(1, np.zeros((10, 3), np.float32))
+    with pytest.raises(HemError):
+        hemctx.build(*c.arrays(), cluster_level=1)
+    assert np.array_equal(hemctx.level(1)["xyz"], want[1]["xyz"])
+    hemctx.clear_outputs()
