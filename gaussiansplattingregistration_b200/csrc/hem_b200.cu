@@ -40,7 +40,7 @@ struct Level {
 };
 
 struct StepStats {
-    int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0;
+    int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0, n_certified = 0;
     double cell_size = 0, max_radius = 0;
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
 };
@@ -60,7 +60,7 @@ struct hem_ctx {
     uint64_t seed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
-    bool timing = false, keep_pairs = false;
+    bool timing = false, keep_pairs = false, smd_prefilter = true;
     double cell_scale = 0.5;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
@@ -75,7 +75,7 @@ struct hem_ctx {
     // workspace (grow-only, reused across steps and builds)
     DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
-    DevBuf radius, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
+    DevBuf radius, psafe, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
     DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh;
     unsigned long long* h_counters = nullptr;   // pinned
@@ -284,11 +284,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     uint32_t* d_pair_cnt = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt);
     float* d_sumlw = (float*)((char*)ctx->ctlbuf.p + off_sumlw);
     CKR(ensure(ctx, ctx->radius, n * 4));
+    CKR(ensure(ctx, ctx->psafe, n));
     CKR(ensure(ctx, ctx->pflag, n * 4));
     CKR(ensure(ctx, ctx->prank, n * 4));
     CK(cudaMemsetAsync(ctx->ctlbuf.p, 0, ctl_bytes, st));
     k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
-        geo, n, distance_delta, ctx->radius.as<float>(), ctx->pflag.as<uint32_t>(), d_ctl);
+        geo, n, distance_delta, ctx->radius.as<float>(), ctx->pflag.as<uint32_t>(), ctx->psafe.as<uint8_t>(), d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
@@ -298,6 +299,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     const Ctl ps = *ctx->h_ctl;
     const int64_t np = (int64_t)ps.n_parents;
     S.n_parents = np;
+    S.n_certified = (int64_t)ps.n_certified;
     float max_radius = 0.0f;
     memcpy(&max_radius, &ps.max_radius_bits, 4);
     S.max_radius = max_radius;
@@ -386,7 +388,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
         k_ptab<<<blocks_for(np, 256), 256, 0, st>>>(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     ctx->radius.as<float>(), geo, (int)np, ctx->ptab.as<uint2>(),
+                                                     ctx->radius.as<float>(), ctx->psafe.as<uint8_t>(), geo, (int)np, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
         size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n / G, 1 << 16));
@@ -407,6 +409,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.cthr = color_delta * color_delta * 0.5f;           // mixture.cpp:123
             A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
+            A.smd_rej = (ctx->smd_prefilter && A.kthr <= 1e4f) ? 2.0f * A.kthr + 0.5f : INFINITY;
             A.pair_cnt_s = d_pair_cnt_s;
             A.pair_cnt = (G == 1) ? d_pair_cnt : nullptr;
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
@@ -414,7 +417,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.counters = d_counters;
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
             if (my_np > 0) {
-                k_gate<<<(unsigned)std::min<int64_t>(blocks_for(my_np, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st>>>(A);
+                k_gate<<<(unsigned)std::min<int64_t>(blocks_for((my_np + GATE_TB - 1) / GATE_TB, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st>>>(A);
                 CK(cudaGetLastError());
                 ctx->n_launches++;
             }
@@ -427,7 +430,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             }
             CK(cudaMemcpyAsync(ctx->h_counters, d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                              // sync B
-            nchunks = ctx->h_counters[C_CHUNK];
+            nchunks = ctx->h_counters[C_POOL] >> POOL_BITS;            // packed: chunks above bit 40, pairs below
+            ctx->h_counters[C_POOL] &= (1ull << POOL_BITS) - 1ull;
             if (ctx->h_counters[C_POOL] <= pool_cap && nchunks <= chunk_cap) break;
             pool_cap = (size_t)ctx->h_counters[C_POOL] + (size_t)ctx->h_counters[C_POOL] / 4 + 1024;
             if (attempt == 7) { ctx->err = "pair pool overflow persisted"; return HEM_ERR_STATE; }
@@ -723,7 +727,7 @@ void hem_destroy(hem_ctx* ctx)
     for (Level& L : ctx->levels) { release(L.geo); release(L.sh); }
     DevBuf* all[] = { &ctx->in_xyz, &ctx->in_col, &ctx->in_op, &ctx->in_cov, &ctx->in_sh, &ctx->in_w, &ctx->in_mask,
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
-                      &ctx->radius, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
+                      &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
@@ -752,6 +756,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     std::string k(name);
     if (k == "timing") ctx->timing = value != 0;
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
+    else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
     else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }
@@ -881,6 +886,7 @@ int hem_step_stats(const hem_ctx* ctx, int step, double* out)
     out[4] = (double)S.n_dropped; out[5] = (double)S.n_out; out[6] = (double)S.grid_cells; out[7] = S.cell_size;
     out[8] = S.max_radius;
     for (int i = 0; i < 9; ++i) out[9 + i] = S.ms[i];
+    out[18] = (double)S.n_certified;
     return HEM_OK;
 }
 

@@ -25,14 +25,14 @@ namespace hem {
 //         q0 = (mean.x, mean.y, mean.z, weight)
 //         q1 = (c00, c01, c02, c11)
 //         q2 = (c12, c22, opacity, det(cov))
-//         q3 = (col.r, col.g, col.b, is_parent as uint bits)
+//         q3 = (col.r, col.g, col.b, uint bits: bit0 = is_parent, bit1 = covariance certified for the smd pre-test)
 //   sh  : F floats per component, unpadded (180-byte rows at SH degree 3), exactly the caller's
 //         [N,F] layout: a device-resident input is used in place and levels are copied out by DMA
 // Cell-sorted working set of a step (index = slot in cell order), SoA float4 planes:
 //   sp0 = (mean.x, mean.y, mean.z, bits(canonical index | is_parent << 31))
 //   sp1 = (col.r, col.g, col.b, opacity)
 //   sp2 = (c00, c01, c02, c11)
-//   sp3 = (c12, c22, det, 0)
+//   sp3 = (c12, c22, det, bits: 1 = covariance certified for the smd pre-test)
 struct GridP {
     float ox, oy, oz, inv_h, h;     // h = 1/inv_h evaluated in FP32 (cell edge used for row culling)
     int gx, gy, gz;
@@ -51,7 +51,7 @@ struct Ctl {
     unsigned int max_radius_bits;   // positive floats order like their bit patterns
     unsigned int n_radius;          // parents with finite positive radius
     unsigned int n_parents;
-    unsigned int pad_;
+    unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
     double sum_radius;
 };
 
@@ -96,8 +96,10 @@ __global__ void k_import(const float* __restrict__ xyz, const float* __restrict_
     bool flag = mask ? (mask[i] != 0) : parent_flag(seed, (uint64_t)i, pp);   // mixture.cpp:330
     geo[4 * i + 0] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w);
     geo[4 * i + 1] = make_float4(c.e00, c.e01, c.e02, c.e11);
-    geo[4 * i + 2] = make_float4(c.e12, c.e22, op[i], det_sym3(c));
-    geo[4 * i + 3] = make_float4(col[3 * i], col[3 * i + 1], col[3 * i + 2], __uint_as_float(flag ? 1u : 0u));
+    const float dt = det_sym3(c);
+    geo[4 * i + 2] = make_float4(c.e12, c.e22, op[i], dt);
+    geo[4 * i + 3] = make_float4(col[3 * i], col[3 * i + 1], col[3 * i + 2],
+                                 __uint_as_float((flag ? 1u : 0u) | (child_cov_certified(c, dt) ? 2u : 0u)));
 }
 
 __global__ void k_export(const float4* __restrict__ geo, int64_t n, float* __restrict__ xyz,
@@ -123,7 +125,7 @@ __global__ void k_export(const float4* __restrict__ geo, int64_t n, float* __res
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* __restrict__ radius,
-       uint32_t* __restrict__ pflag, Ctl* __restrict__ ctl)
+       uint32_t* __restrict__ pflag, uint8_t* __restrict__ psafe, Ctl* __restrict__ ctl)
 {
     // * The FP64 closed-form eigenvalue is ~400 instructions and only one component in
     //   hemReduction is a parent: the parents of a 256-component tile are compacted through
@@ -133,13 +135,14 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     __shared__ float s_cov[256][6];
     __shared__ uint16_t s_src[256];
     __shared__ float s_rad[256];
+    __shared__ uint8_t s_safe[256];
     __shared__ int s_woff[9];
     __shared__ int s_red[8][8];
     __shared__ double s_redd[8];
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
-    unsigned int rbits = 0, rcount = 0, pcount = 0;
+    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0;
     double rsum = 0.0;
     const int64_t ntiles = (n + 255) / 256;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -156,6 +159,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
             if (flag) { q1 = geo[4 * i + 1]; q2 = geo[4 * i + 2]; }
         }
         s_rad[tid] = 0.0f;
+        s_safe[tid] = 0;
         const unsigned bal = __ballot_sync(full, flag);
         if (lane == 0) s_woff[warp + 1] = __popc(bal);
         __syncthreads();
@@ -175,12 +179,16 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
         if (tid == 0) pcount += (unsigned)npar;
         if (tid < npar) {
             const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
-            const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c)));       // mixture.cpp:88
+            double emin, emax;
+            const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c, &emin, &emax)));       // mixture.cpp:88
             if (rad > 0.0f && rad < FLT_MAX) { rbits = max(rbits, __float_as_uint(rad)); rcount += 1; rsum += (double)rad; }
             s_rad[s_src[tid]] = rad;
+            const bool cert = parent_cov_certified(c, det_sym3(c), emin, emax);
+            s_safe[s_src[tid]] = cert ? 1 : 0;
+            ccount += cert ? 1u : 0u;
         }
         __syncthreads();
-        if (i < n) radius[i] = s_rad[tid];
+        if (i < n) { radius[i] = s_rad[tid]; psafe[i] = s_safe[tid]; }
         __syncthreads();
     }
 #pragma unroll
@@ -190,6 +198,8 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     }
     rbits = __reduce_max_sync(full, rbits);
     rcount = __reduce_add_sync(full, rcount);
+    ccount = __reduce_add_sync(full, ccount);
+    if (lane == 0 && ccount) atomicAdd(&ctl->n_certified, ccount);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
     if (lane == 0) {
@@ -248,7 +258,7 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
     sp0[j] = make_float4(q0.x, q0.y, q0.z, __uint_as_float(i | (flag << 31)));
     sp1[j] = make_float4(q3.x, q3.y, q3.z, q2.z);
     sp2[j] = q1;
-    sp3[j] = make_float4(q2.x, q2.y, q2.w, 0.0f);
+    sp3[j] = make_float4(q2.x, q2.y, q2.w, __uint_as_float((__float_as_uint(q3.w) >> 1) & 1u));
     sflag[j] = (uint8_t)flag;
     // segment offsets: cell_start[c] = first slot whose key >= c
     uint32_t lo = (j == 0) ? 0u : skey[j - 1] + 1u;
@@ -267,10 +277,14 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
 #endif
 constexpr int GATE_WARPS = 8;
 constexpr int GATE_OUTCAP = 128;
+constexpr int GATE_TB = 4;                  // parents per work ticket
+// pool and chunk counters share one 64-bit word: pairs in the low 40 bits, chunks above
+constexpr int POOL_BITS = 40;
 
 // per-parent record in cell order, built once per step by k_ptab so that a gate warp starts
 // from ONE contiguous 80-byte read instead of a chain of dependent gathers
-//   [0..3] = sp0..sp3 of the parent's slot, [4] = (radius, weight, bits(canonical rank), bits(canonical index))
+//   [0..3] = sp0..sp3 of the parent's slot,
+//   [4] = (radius, weight, bits(canonical rank | certified << 31), bits(canonical index))
 constexpr int PINFO_F4 = 5;
 
 struct GateArgs {
@@ -280,6 +294,7 @@ struct GateArgs {
     GridP g;
     int t_begin, t_end;          // this rank's slab of parents (cell order)
     float cthr, kthr, decay2;
+    float smd_rej;               // smd pre-test threshold 2*kthr + 0.5 (+inf disables it)
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
     uint32_t* pair_cnt;          // [np+1] same, indexed by canonical rank (single GPU; NULL when sharded)
     uint2* pool; unsigned long long pool_cap;
@@ -290,8 +305,8 @@ struct GateArgs {
 __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __restrict__ sp0,
                        const float4* __restrict__ sp1, const float4* __restrict__ sp2,
                        const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
-                       const float* __restrict__ radius, const float4* __restrict__ geo, int np,
-                       uint2* __restrict__ ptab, float4* __restrict__ pinfo)
+                       const float* __restrict__ radius, const uint8_t* __restrict__ psafe,
+                       const float4* __restrict__ geo, int np, uint2* __restrict__ ptab, float4* __restrict__ pinfo)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= np) return;
@@ -302,7 +317,8 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
     ptab[t] = make_uint2(s, srank);
     float4* o = pinfo + (size_t)t * PINFO_F4;
     o[0] = p0; o[1] = sp1[pj]; o[2] = sp2[pj]; o[3] = sp3[pj];
-    o[4] = make_float4(radius[s], geo[4 * (size_t)s].w, __uint_as_float(srank), __uint_as_float(s));
+    o[4] = make_float4(radius[s], geo[4 * (size_t)s].w, __uint_as_float(srank | ((uint32_t)psafe[s] << 31)),
+                       __uint_as_float(s));
 }
 
 __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
@@ -310,20 +326,26 @@ k_gate(GateArgs A)
 {
     __shared__ uint32_t s_q[GATE_WARPS][64];
     __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
+    __shared__ uint2 s_q2[GATE_WARPS][64];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* q = s_q[warp];
     uint32_t* ob = s_out[warp];
+    uint2* q2 = s_q2[warp];
     const float hc = A.g.h;
     const float INF = __uint_as_float(0x7f800000u);
 
     // persistent warps: parents are handed out in cell order through one ticket counter, so
     // neighbouring warps stream the same cell runs and a heavy parent delays nobody else
     for (;;) {
+        // one ticket = GATE_TB consecutive parents: three same-address atomics per parent (ticket,
+        // pool, chunk) serialised at the L2 and were 13 % of the kernel's stall samples
         unsigned long long ticket = 0;
         if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
-        const int t = A.t_begin + (int)__shfl_sync(full, ticket, 0);
-        if (t >= A.t_end) break;
+        const int tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * GATE_TB;
+        if (tfirst >= A.t_end) break;
+        const int tlast = min(tfirst + GATE_TB, A.t_end);
+      for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
         const float4 p0 = pi[0], p1 = pi[1], p2 = pi[2], p3 = pi[3], p4 = pi[4];
@@ -335,7 +357,8 @@ k_gate(GateArgs A)
         const float pdet = p3.z;
         const Sym3 ip = inverse_sym3(pc, pdet);
 
-        int qn = 0, on = 0;
+        const bool pcert = (__float_as_uint(p4.z) >> 31) != 0;
+        int qn = 0, q2n = 0, on = 0;
         uint32_t total_out = 0;
 
         // accepted children wait in `ob` as sorted slots; the likelihood is evaluated here, on
@@ -344,8 +367,9 @@ k_gate(GateArgs A)
             if (on > 0) {
                 unsigned long long base = 0, cid = 0;
                 if (lane == 0) {
-                    base = atomicAdd(&A.counters[C_POOL], (unsigned long long)on);
-                    cid = atomicAdd(&A.counters[C_CHUNK], 1ull);
+                    const unsigned long long v = atomicAdd(&A.counters[C_POOL], (1ull << POOL_BITS) | (unsigned long long)on);
+                    base = v & ((1ull << POOL_BITS) - 1ull);
+                    cid = v >> POOL_BITS;
                 }
                 base = __shfl_sync(full, base, 0);
                 const bool room = base + (unsigned long long)on <= A.pool_cap;
@@ -371,35 +395,62 @@ k_gate(GateArgs A)
         };
 
         // candidates that passed the radius + parent-exclusion test: colour gate, KLD gate, likelihood
-        auto process = [&](int m) {
+        // stage B: candidates that survived colour gate and smd pre-test: trace, log-det, KLD gate
+        auto stage_b = [&](int m) {
             bool acc = false;
             uint32_t jj = 0;
             if (lane < m) {
-                jj = q[lane];
-                // all four planes are requested at once (the colour gate rejects only ~1 in 5)
-                const float4 c1 = A.sp1[jj], c0 = A.sp0[jj], c2 = A.sp2[jj], c3 = A.sp3[jj];
-                // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
-                const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
-                if (!(cdist > A.cthr)) {
-                    // KLD(child || parent), gaussian.hpp:106-109
-                    const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
-                    const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
-                    const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
-                    const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
-                    const float smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
-                    const float t00 = fa(fa(fm(c2.x, ip.e00), fm(c2.y, ip.e01)), fm(c2.z, ip.e02));
-                    const float t11 = fa(fa(fm(c2.y, ip.e01), fm(c2.w, ip.e11)), fm(c3.x, ip.e12));
-                    const float t22 = fa(fa(fm(c2.z, ip.e02), fm(c3.x, ip.e12)), fm(c3.y, ip.e22));
-                    const float tr = fa(fa(t00, t11), t22);
-                    const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(c3.z, pdet))));
-                    acc = !(kl > A.kthr);
-                }
+                const uint2 e = q2[lane];
+                jj = e.x;
+                const float smd = __uint_as_float(e.y);
+                const float4 c2 = A.sp2[jj], c3 = A.sp3[jj];
+                const float t00 = fa(fa(fm(c2.x, ip.e00), fm(c2.y, ip.e01)), fm(c2.z, ip.e02));
+                const float t11 = fa(fa(fm(c2.y, ip.e01), fm(c2.w, ip.e11)), fm(c3.x, ip.e12));
+                const float t22 = fa(fa(fm(c2.z, ip.e02), fm(c3.x, ip.e12)), fm(c3.y, ip.e22));
+                const float tr = fa(fa(t00, t11), t22);
+                // KLD(child || parent), gaussian.hpp:106-109
+                const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(c3.z, pdet))));
+                acc = !(kl > A.kthr);
             }
             const unsigned am = __ballot_sync(full, acc);
             if (acc) ob[on + __popc(am & ((1u << lane) - 1u))] = jj;
             on += __popc(am);
             __syncwarp();
             if (on > GATE_OUTCAP - 32) flush();
+        };
+        // stage A: candidates that passed the radius + parent-exclusion test: colour gate, squared
+        // Mahalanobis distance, certified pre-test (hem_math.cuh); survivors queue for stage B
+        auto process = [&](int m) {
+            bool keep = false;
+            uint32_t jj = 0;
+            float smd = 0.0f;
+            if (lane < m) {
+                jj = q[lane];
+                const float4 c1 = A.sp1[jj], c0 = A.sp0[jj];
+                const uint32_t ccert = __float_as_uint(A.sp3[jj].w);
+                // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
+                const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
+                if (!(cdist > A.cthr)) {
+                    const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
+                    const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
+                    const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
+                    const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
+                    smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
+                    keep = !(pcert && ccert != 0u && smd > A.smd_rej);
+                }
+            }
+            const unsigned km = __ballot_sync(full, keep);
+            if (keep) q2[q2n + __popc(km & ((1u << lane) - 1u))] = make_uint2(jj, __float_as_uint(smd));
+            q2n += __popc(km);
+            __syncwarp();
+            if (q2n >= 32) {
+                stage_b(32);
+                const uint2 mv = (lane + 32 < q2n) ? q2[lane + 32] : make_uint2(0u, 0u);
+                __syncwarp();
+                q2[lane] = mv;
+                q2n -= 32;
+                __syncwarp();
+            }
         };
 
         if (rad > 0.0f) {        // NaN / zero radius: no child can pass `d2 < r*r` (pointindex.cpp:138)
@@ -497,13 +548,15 @@ k_gate(GateArgs A)
                 }
             }
             if (qn > 0) process(qn);
+            if (q2n > 0) stage_b(q2n);
             flush();
         }
         if (lane == 0) {
             A.pair_cnt_s[t] = total_out;
-            if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z)] = total_out;
+            if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
         }
         __syncwarp();
+      }
     }
 }
 
@@ -760,8 +813,9 @@ __global__ void k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* _
             q2.w = dt;
             geo[4 * j + 2] = q2;
         }
-        reinterpret_cast<float*>(geo)[16 * j + 15] =
-            __uint_as_float(parent_flag(seed, rng_base + (uint64_t)j, pp) ? 1u : 0u);
+        const Sym3 cc = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
+        reinterpret_cast<float*>(geo)[16 * j + 15] = __uint_as_float(
+            (parent_flag(seed, rng_base + (uint64_t)j, pp) ? 1u : 0u) | (child_cov_certified(cc, dt) ? 2u : 0u));
         bad = (q0.x != q0.x || q0.y != q0.y || q0.z != q0.z) || (dt != dt) || dt <= 0.0f;
         valid[j] = bad ? 0 : 1;
     }

@@ -111,7 +111,7 @@ __device__ __forceinline__ float logf_glibc(float x)
 // atan2/sin/cos are not bit-identical to glibc's; a last-bit difference of the
 // double survives the cast to float with probability ~2^-29.
 // --------------------------------------------------------------------------
-__device__ __forceinline__ float eig_max_sym3(const Sym3& m)
+__device__ __forceinline__ float eig_max_sym3(const Sym3& m, double* emin_out = nullptr, double* emax_out = nullptr)
 {
     const double inv3 = 0.33333333333333333333333333333333;
     const double root3 = 1.7320508075688772935274463415059;
@@ -140,7 +140,60 @@ __device__ __forceinline__ float eig_max_sym3(const Sym3& m)
     if (e2 < e1) { h = e1; e1 = e2; e2 = h; }
     if (e1 < e0) { h = e0; e0 = e1; e1 = h; }
     if (e2 < e1) { h = e1; e1 = e2; e2 = h; }
+    if (emin_out) *emin_out = e0;
+    if (emax_out) *emax_out = e2;
     return (float)e2;
+}
+
+// --------------------------------------------------------------------------
+// Certificates for the Mahalanobis pre-test of the KLD gate (DESIGN.md "smd pre-test").
+//
+// For symmetric positive definite P (parent) and C (child), exact arithmetic gives
+//     tr(P^-1 C) - 3 - ln(det C / det P) >= 0            (AM-GM on the eigenvalues of P^-1 C),
+// so KLD = 0.5 (smd + tr - 3 - ln) > kthr as soon as smd > 2 kthr.  The reference evaluates the
+// formula in FP32; the pre-test may only replace that evaluation where the FP32 values provably
+// stay close to the exact ones.  Both certificates are MEASURED per component in FP64 (no
+// worst-case bounds):
+//   child  : C finite and positive definite (Sylvester, FP64), |det_f - det| <= 1e-3 det
+//   parent : P positive definite, |det_f - det| <= 1e-3 det, and with ip = the FP32 inverse the
+//            gate uses, E = ip - P^-1:  eta = ||E||_F * lambda_max(P) + 2e-6 * kappa_ub(P) <= 0.01,
+//            kappa_ub = lambda_max^3 / det >= kappa (lambda_max itself is accurate: it defines the radius)
+// Then |tr(E C)| <= ||E||_2 tr(C) <= eta tr(P^-1 C), the FP32 dot products add <= 2e-6 kappa
+// relative, |ln_f - ln| <= 2.1e-3, hence tr_f - 3 - ln_f >= 3 ln(1 - eta) - 2.1e-3 >= -0.033 and
+// the FP32 KLD exceeds kthr whenever smd_f > 2 kthr + 0.5 (kthr <= 1e4; the margin also covers the
+// three FP32 additions of the formula).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double det_sym3_d(const Sym3& c)
+{
+    const double e00 = c.e00, e01 = c.e01, e02 = c.e02, e11 = c.e11, e12 = c.e12, e22 = c.e22;
+    return e00 * (e11 * e22 - e12 * e12) - e01 * (e01 * e22 - e12 * e02) + e02 * (e01 * e12 - e11 * e02);
+}
+
+__device__ __forceinline__ bool child_cov_certified(const Sym3& c, float det_f)
+{
+    const double e00 = c.e00, e01 = c.e01, e11 = c.e11;
+    const double m2 = e00 * e11 - e01 * e01;
+    const double dt = det_sym3_d(c);
+    // NaN / inf anywhere makes one of the comparisons false
+    const bool fin = (fabs(dt) < 1.7e308) && (fabsf(c.e22) < 3.0e38f) && (fabsf(c.e02) < 3.0e38f) && (fabsf(c.e12) < 3.0e38f);
+    return fin && e00 > 0.0 && m2 > 0.0 && dt > 0.0 && fabs((double)det_f - dt) <= 1e-3 * dt;
+}
+
+__device__ __forceinline__ bool parent_cov_certified(const Sym3& c, float det_f, double emin, double emax)
+{
+    (void)emin;     // the closed form's smallest root is unreliable for ill-conditioned input: not used
+    if (!(emax > 0.0) || !(emax < 1.7e308) || !child_cov_certified(c, det_f)) return false;
+    const double dt = det_sym3_d(c);
+    emax *= 1.001;
+    const Sym3 ip = inverse_sym3(c, det_f);           // exactly what k_gate computes
+    const double e00 = c.e00, e01 = c.e01, e02 = c.e02, e11 = c.e11, e12 = c.e12, e22 = c.e22;
+    const double id = 1.0 / dt;
+    const double d00 = (e11 * e22 - e12 * e12) * id - ip.e00, d01 = (e02 * e12 - e01 * e22) * id - ip.e01;
+    const double d02 = (e01 * e12 - e02 * e11) * id - ip.e02, d11 = (e00 * e22 - e02 * e02) * id - ip.e11;
+    const double d12 = (e02 * e01 - e00 * e12) * id - ip.e12, d22 = (e00 * e11 - e01 * e01) * id - ip.e22;
+    const double fro = sqrt(d00 * d00 + d11 * d11 + d22 * d22 + 2.0 * (d01 * d01 + d02 * d02 + d12 * d12));
+    const double eta = fro * emax + 2e-6 * (emax * emax * emax / dt);
+    return eta <= 0.01;
 }
 
 // --------------------------------------------------------------------------

@@ -58,7 +58,9 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
 /* Options (all optional):
  *   "timing"      1 -> record CUDA events around every stage (hem_step_stats ms fields)
  *   "keep_pairs"  1 -> retain each step's (parent, child, wL) lists for hem_step_pairs
- *   "cell_scale"  grid cell = cell_scale * mean parent radius (default 1.0)
+ *   "cell_scale"  grid cell = cell_scale * mean parent radius (default 0.5)
+ *   "smd_prefilter" 1 (default) -> certified Mahalanobis pre-test inside the KLD gate (same
+ *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
  *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
  *                 (the reference consumes one draw per level-0 component first,
  *                 src/cpp_ext/src/mixture.cpp:330, then one per pre-filter
@@ -118,9 +120,10 @@ int hem_clear_outputs(hem_ctx* ctx);
  *   6 grid_cells  7 cell_size  8 max_radius
  *   9 ms_total  10 ms_prep  11 ms_grid  12 ms_gate  13 ms_sumlw  14 ms_moments  15 ms_compact
  *   16 ms_k_gate (the gate kernel alone)  17 ms_k_moments (the moment kernel alone)
+ *   18 n_certified_parents (parents whose covariance is certified for the smd pre-test)
  * ms_* are CUDA-event times on the context's stream and are 0 unless the
  * "timing" option is set. */
-#define HEM_STEP_STATS_LEN 18
+#define HEM_STEP_STATS_LEN 19
 int hem_step_stats(const hem_ctx* ctx, int step, double* out);
 
 /* Cumulative counters of the context: "launches" (kernels of this library

@@ -251,3 +251,35 @@ def test_gpu_bound_outputs_and_host_upload_overlap(hemctx):
         hemctx.build(*c.arrays(), cluster_level=1)
     assert np.array_equal(hemctx.level(1)["xyz"], want[1]["xyz"])
     hemctx.clear_outputs()
+
+
+@pytest.mark.parametrize("kind", ["benchmark", "anisotropic", "degenerate"])
+def test_gpu_smd_prefilter_never_changes_membership(kind):
+    """The certified Mahalanobis pre-test (hem_math.cuh) is an evaluation shortcut: with it on
+    or off the accepted (parent, child) pairs, wL and every output must be bit-identical."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    if kind == "benchmark":
+        c = synth(60000, seed=71, density=5000.0)
+    elif kind == "anisotropic":        # needle / disc splats, condition numbers up to ~1e6
+        c = synth(40000, seed=72, density=20000.0, scale_sigma_ln=1.5, clip_sigma=None)
+    else:
+        g = load_golden("degenerate_sh0")
+        from gaussiansplattingregistration_b200.synth import SplatCloud
+        c = SplatCloud(g["xyz"], g["colors"], g["opacity"], g["cov6"], g["sh"])
+    res = []
+    for on in (1, 0):
+        with HemContext(0, seed=7) as ctx:
+            ctx.set_option("keep_pairs", 1)
+            ctx.set_option("smd_prefilter", on)
+            ctx.build(*c.arrays(), cluster_level=2)
+            res.append(([ctx.level(l, True) for l in range(3)], [ctx.step_pairs(s) for s in range(2)],
+                        ctx.step_stats(0)))
+    (la, pa, sa), (lb, pb, sb) = res
+    if kind == "benchmark":
+        assert sa["n_certified_parents"] > 0.9 * sa["n_parents"]
+    for s in range(2):
+        for k in ("parent_idx", "off", "child", "wl", "sumlw"):
+            assert np.array_equal(pa[s][k], pb[s][k], equal_nan=True), f"{kind}: step {s} {k} differs with the pre-test"
+    for l in range(3):
+        for k in KEYS:
+            assert np.array_equal(la[l][k], lb[l][k], equal_nan=True), f"{kind}: level {l} {k} differs with the pre-test"
