@@ -61,6 +61,7 @@ struct hem_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     bool timing = false, keep_pairs = false, smd_prefilter = true;
+    int sumlw_mode = 0;            // 0 auto, 1 radix sort, 2 claim table
     double cell_scale = 0.5;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
@@ -77,7 +78,7 @@ struct hem_ctx {
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
     DevBuf radius, psafe, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh;
+    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned
     cudaEvent_t ev[EV_COUNT] = {};
@@ -273,16 +274,18 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
 
     // ---- S1 prep --------------------------------------------------------------------------
     // control block + the arrays that must start from zero live in one allocation: one memset per step
-    //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) ]
+    //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) | cnt_c (n) ]
     const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
     const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
-    const size_t ctl_bytes = off_sumlw + (size_t)n * 4;
+    const size_t off_cntc = off_sumlw + ((size_t)n * 4 + 255) / 256 * 256;
+    const size_t ctl_bytes = off_cntc + (size_t)n * 4;
     CKR(ensure(ctx, ctx->ctlbuf, ctl_bytes));
     Ctl* d_ctl = ctx->ctlbuf.as<Ctl>();
     unsigned long long* d_counters = d_ctl->counters;
     uint32_t* d_pair_cnt_s = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt_s);
     uint32_t* d_pair_cnt = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt);
     float* d_sumlw = (float*)((char*)ctx->ctlbuf.p + off_sumlw);
+    uint32_t* d_cnt_c = (uint32_t*)((char*)ctx->ctlbuf.p + off_cntc);
     CKR(ensure(ctx, ctx->radius, n * 4));
     CKR(ensure(ctx, ctx->psafe, n));
     CKR(ensure(ctx, ctx->pflag, n * 4));
@@ -411,7 +414,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
             A.smd_rej = (ctx->smd_prefilter && A.kthr <= 1e4f) ? 2.0f * A.kthr + 0.5f : INFINITY;
             A.pair_cnt_s = d_pair_cnt_s;
-            A.pair_cnt = (G == 1) ? d_pair_cnt : nullptr;
+            A.pair_cnt = (G == 1) ? d_pair_cnt : nullptr;      // used only by the canonical-CSR (sort / white-box) path
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
             A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
             A.counters = d_counters;
@@ -464,24 +467,39 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
-        if (G > 1) {        // sharded: counts arrive in cell order, put them in canonical order here
-            k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), d_pair_cnt_s, (int)np, d_pair_cnt);
-            CK(cudaGetLastError()); ctx->n_launches++;
-        }
-        CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
-            return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt, ctx->pair_off.as<uint32_t>(),
-                                                 (int)(np + 1), st);
-        }));
-        if (P > 0) {
-            k_csr_canon<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
-                                                                   ctx->pair_off.as<uint32_t>(), ctx->csr_s.as<uint2>(), (int)np,
-                                                                   ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
-            CK(cudaGetLastError()); ctx->n_launches++;
-        }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
-        if (P > 0) {
+        // sparse regime (the benchmark's): claim table, 2 launches; dense regime: stable radix sort of the
+        // canonical CSR by child.  Both add a child's claims in ascending parent rank (bit-identical).
+        const bool use_claims = ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
+        const bool need_canon = !use_claims || ctx->keep_pairs;
+        if (need_canon) {
+            if (G > 1) {    // sharded: counts arrive in cell order, put them in canonical order here
+                k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), d_pair_cnt_s, (int)np, d_pair_cnt);
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
+            CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
+                return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt, ctx->pair_off.as<uint32_t>(), (int)(np + 1), st);
+            }));
+            if (P > 0) {
+                k_csr_canon<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                                                                       ctx->pair_off.as<uint32_t>(), ctx->csr_s.as<uint2>(), (int)np,
+                                                                       ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
+        }
+        if (P > 0 && use_claims) {
+            CKR(ensure(ctx, ctx->claims, (size_t)n * CLAIM_K * 8));
+            CKR(ensure(ctx, ctx->ovf, (size_t)P * 16));
+            k_claims<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                                                                ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
+                                                                ctx->ovf.as<uint4>(), (unsigned long long)P, d_counters);
+            CK(cudaGetLastError()); ctx->n_launches++;
+            k_sumlw_claims<<<blocks_for(n, 256), 256, 0, st>>>(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
+                                                                n, d_sumlw);
+            CK(cudaGetLastError()); ctx->n_launches++;
+        } else if (P > 0) {
             CKR(ensure(ctx, ctx->sk, P * 4));
             CKR(ensure(ctx, ctx->sv, P * 4));
             const int cbits = bits_for((uint64_t)n - 1);
@@ -489,8 +507,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 return cub::DeviceRadixSort::SortPairs(tt, bb, ctx->csr_child.as<uint32_t>(), ctx->sk.as<uint32_t>(),
                                                        ctx->csr_wl.as<float>(), ctx->sv.as<float>(), (int)P, 0, cbits, st);
             }));
-            k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P,
-                                                          d_sumlw);
+            k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
@@ -731,7 +748,7 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh };
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf };
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -757,6 +774,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     if (k == "timing") ctx->timing = value != 0;
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
+    else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
     else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }

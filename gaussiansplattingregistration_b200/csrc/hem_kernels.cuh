@@ -40,7 +40,7 @@ struct GridP {
 
 // Per-step control block.  Everything in it (and the per-parent / per-child arrays that follow
 // it in the same allocation) starts from zero, so ONE memset opens a step.
-enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_WORK = 4, C_WORK2 = 5, C_COUNT = 8 };
+enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_WORK = 4, C_WORK2 = 5, C_OVF = 6, C_COUNT = 8 };
 
 struct Ctl {
     unsigned long long counters[C_COUNT];
@@ -598,6 +598,85 @@ __global__ void k_csr_canon(const uint2* __restrict__ ptab, const uint32_t* __re
         csr_child[dst + (k - a)] = p.x;
         csr_wl[dst + (k - a)] = __uint_as_float(p.y);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Per-child normaliser sumLw, claim-table path (sparse regime, <= 4 claims per child on
+// average): every accepted pair drops (parent rank, wL) into one of CLAIM_K slots of its child
+// (slot = atomic counter, order irrelevant), then one thread per child adds its claims in
+// ASCENDING PARENT RANK — the reference's order (mixture.cpp:143-163) — so the result is
+// bit-identical to the sort path and run-to-run deterministic.  Claims beyond CLAIM_K go to a
+// global overflow list that the child scans (never reached at the benchmark densities).
+// ---------------------------------------------------------------------------
+constexpr int CLAIM_K = 16;
+
+__global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
+                         const uint2* __restrict__ csr_s, int np, uint32_t* __restrict__ cnt_c,
+                         uint2* __restrict__ claims, uint4* __restrict__ ovf, unsigned long long ovf_cap,
+                         unsigned long long* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (t >= np) return;
+    const uint32_t a = pair_off_s[t], e = pair_off_s[t + 1];
+    const uint32_t srank = ptab[t].y;
+    for (uint32_t k = a + lane; k < e; k += 32) {
+        const uint2 p = csr_s[k];
+        const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
+        if (slot < (uint32_t)CLAIM_K) {
+            claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
+        } else {
+            const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+            if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
+        }
+    }
+}
+
+__global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ claims,
+                               const uint4* __restrict__ ovf, const unsigned long long* __restrict__ counters,
+                               int64_t n, float* __restrict__ sumlw)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t m = cnt_c[c];
+    if (m == 0) return;                                  // orphan: sumLw stays exactly 0
+    const uint2* row = claims + (size_t)c * CLAIM_K;
+    if (m <= 4) {
+        // common case: the claims sit in registers (two 16-byte loads), sorted by a 4-element network
+        const uint4 a = reinterpret_cast<const uint4*>(row)[0];
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (m > 2) b = reinterpret_cast<const uint4*>(row)[1];
+        uint32_t k0 = a.x, k1 = m > 1 ? a.z : 0xffffffffu, k2 = m > 2 ? b.x : 0xffffffffu, k3 = m > 3 ? b.z : 0xffffffffu;
+        uint32_t w0 = a.y, w1 = a.w, w2 = b.y, w3 = b.w;
+#define HEM_CSWAP(ka, wa, kb, wb) { if (kb < ka) { uint32_t t_ = ka; ka = kb; kb = t_; t_ = wa; wa = wb; wb = t_; } }
+        HEM_CSWAP(k0, w0, k1, w1) HEM_CSWAP(k2, w2, k3, w3) HEM_CSWAP(k0, w0, k2, w2) HEM_CSWAP(k1, w1, k3, w3) HEM_CSWAP(k1, w1, k2, w2)
+#undef HEM_CSWAP
+        float s = __uint_as_float(w0);                   // 0 + w0 == w0 exactly (w0 > 0)
+        if (m > 1) s = fa(s, __uint_as_float(w1));
+        if (m > 2) s = fa(s, __uint_as_float(w2));
+        if (m > 3) s = fa(s, __uint_as_float(w3));
+        sumlw[c] = s;
+        return;
+    }
+    const uint32_t mt = min(m, (uint32_t)CLAIM_K);
+    const unsigned long long nov = (m > (uint32_t)CLAIM_K) ? counters[C_OVF] : 0ull;
+    float s = 0.0f;
+    long long last = -1;
+    for (uint32_t i = 0; i < m; ++i) {                   // selection by ascending parent rank
+        long long best = 0x7fffffffffffffffll;
+        float bw = 0.0f;
+        for (uint32_t k = 0; k < mt; ++k) {
+            const uint2 e = row[k];
+            if ((long long)e.x > last && (long long)e.x < best) { best = e.x; bw = __uint_as_float(e.y); }
+        }
+        for (unsigned long long k = 0; k < nov; ++k) {
+            const uint4 e = ovf[k];
+            if (e.x == (uint32_t)c && (long long)e.y > last && (long long)e.y < best) { best = e.y; bw = __uint_as_float(e.z); }
+        }
+        s = fa(s, bw);
+        last = best;
+    }
+    sumlw[c] = s;
 }
 
 // per-child normaliser: pairs stably sorted by child (parents ascending inside a

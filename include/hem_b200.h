@@ -61,6 +61,8 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *   "cell_scale"  grid cell = cell_scale * mean parent radius (default 0.5)
  *   "smd_prefilter" 1 (default) -> certified Mahalanobis pre-test inside the KLD gate (same
  *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
+ *   "sumlw_mode"  0 (default) auto, 1 stable radix sort by child, 2 claim table: two bit-identical
+ *                 ways of adding a child's claims in ascending parent order
  *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
  *                 (the reference consumes one draw per level-0 component first,
  *                 src/cpp_ext/src/mixture.cpp:330, then one per pre-filter

@@ -283,3 +283,28 @@ def test_gpu_smd_prefilter_never_changes_membership(kind):
     for l in range(3):
         for k in KEYS:
             assert np.array_equal(la[l][k], lb[l][k], equal_nan=True), f"{kind}: level {l} {k} differs with the pre-test"
+
+
+@pytest.mark.parametrize("density", [5000.0, 100000.0])
+def test_gpu_sumlw_paths_bit_identical(density):
+    """sumLw by claim table and by stable radix sort must agree bit for bit (both add a child's
+    claims in ascending parent order), in the sparse and in the dense regime (claim overflow)."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(30000, seed=81, density=density)
+    res = []
+    for mode in (1, 2):
+        with HemContext(0, seed=7) as ctx:
+            ctx.set_option("keep_pairs", 1)
+            ctx.set_option("sumlw_mode", mode)
+            ctx.build(*c.arrays(), cluster_level=2)
+            res.append(([ctx.level(l, True) for l in range(3)], [ctx.step_pairs(s) for s in range(2)]))
+    (la, pa), (lb, pb) = res
+    if density > 50000:
+        cnt = np.bincount(pa[0]["child"], minlength=30000)
+        assert cnt.max() > 16, "dense case must exercise the claim overflow list"
+    for s in range(2):
+        assert np.array_equal(pa[s]["sumlw"], pb[s]["sumlw"]), f"step {s}: sumLw differs between the two paths"
+        assert np.array_equal(pa[s]["child"], pb[s]["child"])
+    for l in range(3):
+        for k in KEYS:
+            assert np.array_equal(la[l][k], lb[l][k]), f"level {l} {k} differs between the two sumLw paths"
