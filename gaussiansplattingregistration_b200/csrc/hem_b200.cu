@@ -164,14 +164,22 @@ int bits_for(uint64_t max_value)
 
 template <class F> int cub_call(hem_ctx* ctx, F&& f)
 {
+    // CUB's two-phase protocol costs a second host-side dispatch per call, which matters on the
+    // small (launch-bound) levels: with a warm temp buffer the call goes straight through and the
+    // size query only runs if CUB reports the buffer as too small.
+    if (ctx->cubtmp.p && ctx->cubtmp.cap >= (size_t)8 << 20) {
+        size_t have = ctx->cubtmp.cap;
+        cudaError_t e = f(ctx->cubtmp.p, have);
+        if (e == cudaSuccess) return HEM_OK;
+        cudaGetLastError();
+    }
     size_t bytes = 0;
     CK(f((void*)nullptr, bytes));
-    CKR(ensure(ctx, ctx->cubtmp, bytes));
+    CKR(ensure(ctx, ctx->cubtmp, std::max<size_t>(bytes, (size_t)8 << 20)));
     size_t have = ctx->cubtmp.cap;
     CK(f(ctx->cubtmp.p, have));
     return HEM_OK;
 }
-
 
 // ---------------------------------------------------------------------------
 // NCCL, resolved at run time (dlopen) so that the single-GPU library has no NCCL
@@ -391,7 +399,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
         k_ptab<<<blocks_for(np, 256), 256, 0, st>>>(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     ctx->radius.as<float>(), ctx->psafe.as<uint8_t>(), geo, (int)np, ctx->ptab.as<uint2>(),
+                                                     ctx->radius.as<float>(), ctx->psafe.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
         size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n / G, 1 << 16));

@@ -285,7 +285,9 @@ constexpr int POOL_BITS = 40;
 // from ONE contiguous 80-byte read instead of a chain of dependent gathers
 //   [0..3] = sp0..sp3 of the parent's slot,
 //   [4] = (radius, weight, bits(canonical rank | certified << 31), bits(canonical index))
-constexpr int PINFO_F4 = 5;
+//   [5] = (ip00, ip01, ip02, ip11)   the FP32 inverse covariance of the KLD gate, computed once per
+//   [6] = (ip12, ip22, bits(y0 | y1 << 16), bits(z0 | z1 << 16))   parent by a THREAD instead of a warp
+constexpr int PINFO_F4 = 7;
 
 struct GateArgs {
     const float4* sp0; const float4* sp1; const float4* sp2; const float4* sp3;
@@ -302,23 +304,44 @@ struct GateArgs {
     unsigned long long* counters;
 };
 
+// conservative cell box of a parent's search sphere along one axis (DESIGN.md "grid range")
+__device__ __forceinline__ void cell_range(float q, float rr, float o, float inv_h, int g, int& lo, int& hi)
+{
+    const float pad = (fabsf(q) + rr) * 2.4e-7f;
+    lo = cell_axis(q - (rr + pad), o, inv_h, g);
+    hi = cell_axis(q + (rr + pad), o, inv_h, g);
+}
+
 __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __restrict__ sp0,
                        const float4* __restrict__ sp1, const float4* __restrict__ sp2,
                        const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
                        const float* __restrict__ radius, const uint8_t* __restrict__ psafe,
-                       const float4* __restrict__ geo, int np, uint2* __restrict__ ptab, float4* __restrict__ pinfo)
+                       const float4* __restrict__ geo, GridP g, int np, uint2* __restrict__ ptab,
+                       float4* __restrict__ pinfo)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= np) return;
     const uint32_t pj = psorted[t];
-    const float4 p0 = sp0[pj];
+    const float4 p0 = sp0[pj], p2 = sp2[pj], p3 = sp3[pj];
     const uint32_t s = __float_as_uint(p0.w) & 0x7fffffffu;
     const uint32_t srank = prank[s];
+    const float rad = radius[s];
     ptab[t] = make_uint2(s, srank);
+    const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
+    const Sym3 ip = inverse_sym3(pc, p3.z);
+    int y0 = 0, y1 = 0, z0 = 0, z1 = 0;
+    if (rad > 0.0f) {
+        const float rr = rad * 1.00001f;
+        cell_range(p0.y, rr, g.oy, g.inv_h, g.gy, y0, y1);
+        cell_range(p0.z, rr, g.oz, g.inv_h, g.gz, z0, z1);
+    }
     float4* o = pinfo + (size_t)t * PINFO_F4;
-    o[0] = p0; o[1] = sp1[pj]; o[2] = sp2[pj]; o[3] = sp3[pj];
-    o[4] = make_float4(radius[s], geo[4 * (size_t)s].w, __uint_as_float(srank | ((uint32_t)psafe[s] << 31)),
+    o[0] = p0; o[1] = sp1[pj]; o[2] = p2; o[3] = p3;
+    o[4] = make_float4(rad, geo[4 * (size_t)s].w, __uint_as_float(srank | ((uint32_t)psafe[s] << 31)),
                        __uint_as_float(s));
+    o[5] = make_float4(ip.e00, ip.e01, ip.e02, ip.e11);
+    o[6] = make_float4(ip.e12, ip.e22, __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
+                       __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
 }
 
 __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
@@ -348,14 +371,13 @@ k_gate(GateArgs A)
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
-        const float4 p0 = pi[0], p1 = pi[1], p2 = pi[2], p3 = pi[3], p4 = pi[4];
+        const float4 p0 = pi[0], p1 = pi[1], p3 = pi[3], p4 = pi[4], p5 = pi[5], p6 = pi[6];
         const uint32_t s = __float_as_uint(p4.w);
         const float rad = p4.x;
         const float pw = p4.y;
         const float r2 = fm(rad, rad);
-        const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
         const float pdet = p3.z;
-        const Sym3 ip = inverse_sym3(pc, pdet);
+        const Sym3 ip = { p5.x, p5.y, p5.z, p5.w, p6.x, p6.y };
 
         const bool pcert = (__float_as_uint(p4.z) >> 31) != 0;
         int qn = 0, q2n = 0, on = 0;
@@ -458,11 +480,8 @@ k_gate(GateArgs A)
             // |d| <= rad*(1+5*2^-24) per axis; pads cover the rounding of the range ends themselves
             const float rr = rad * 1.00001f;
             const float rr2 = rr * rr;
-            const float pady = (fabsf(p0.y) + rr) * 2.4e-7f, padz = (fabsf(p0.z) + rr) * 2.4e-7f;
-            const int y0 = cell_axis(p0.y - (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
-            const int y1 = cell_axis(p0.y + (rr + pady), A.g.oy, A.g.inv_h, A.g.gy);
-            const int z0 = cell_axis(p0.z - (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
-            const int z1 = cell_axis(p0.z + (rr + padz), A.g.oz, A.g.inv_h, A.g.gz);
+            const int y0 = (int)(__float_as_uint(p6.z) & 0xffffu), y1 = (int)(__float_as_uint(p6.z) >> 16);
+            const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
 
