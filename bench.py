@@ -59,40 +59,73 @@ def workload_config(a, world):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML is polled from a thread
+    every ~2 ms (the timed region of the default run is tens of milliseconds; `nvidia-smi -lms`
+    needs longer than that to print its first line and is only the fallback)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.idx = gpu_index
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._stop = threading.Event()
         self.thread = None
+        self.nvml = None
+        self.proc = None
+        self.rows = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
-        self.thread.start()
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        self._stop.set()
+        if self.nvml is not None:
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, polled during the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source available"]}
         time.sleep(0.15)
         self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx = [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -105,9 +138,9 @@ class ClockSampler:
                 continue
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
+                    self.reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(self.reasons), "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------- CPU reference leg

@@ -37,6 +37,7 @@ struct Level {
     DevBuf geo;              // float4[4*cap]
     DevBuf sh;               // float[cap*F], owned storage
     const float* shp = nullptr;   // where the SH rows are: sh.p, or the caller's device array (level 0, in place)
+    DevBuf ex_xyz, ex_col, ex_op, ex_cov;   // de-interleaved copy for a bound host output (DMA source)
 };
 
 struct StepStats {
@@ -80,7 +81,8 @@ struct hem_ctx {
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
     DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf;
     unsigned long long* h_counters = nullptr;   // pinned
-    Ctl* h_ctl = nullptr;                       // pinned
+    Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
+    Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
     cudaEvent_t ev[EV_COUNT] = {};
 
     // copy/compute overlap: SH rows arrive and finished levels leave on a second stream
@@ -286,7 +288,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
     const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
     const size_t off_cntc = off_sumlw + ((size_t)n * 4 + 255) / 256 * 256;
-    const size_t ctl_bytes = off_cntc + (size_t)n * 4;
+    const size_t ctl_bytes = (off_cntc + (size_t)n * 4 + 15) / 16 * 16;
     CKR(ensure(ctx, ctx->ctlbuf, ctl_bytes));
     Ctl* d_ctl = ctx->ctlbuf.as<Ctl>();
     unsigned long long* d_counters = d_ctl->counters;
@@ -298,14 +300,16 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CKR(ensure(ctx, ctx->psafe, n));
     CKR(ensure(ctx, ctx->pflag, n * 4));
     CKR(ensure(ctx, ctx->prank, n * 4));
-    CK(cudaMemsetAsync(ctx->ctlbuf.p, 0, ctl_bytes, st));
+    k_zero<<<(unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
+    CK(cudaGetLastError()); ctx->n_launches++;
     k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
         geo, n, distance_delta, ctx->radius.as<float>(), ctx->pflag.as<uint32_t>(), ctx->psafe.as<uint8_t>(), d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
     }));
-    CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));                                      // sync A
     const Ctl ps = *ctx->h_ctl;
     const int64_t np = (int64_t)ps.n_parents;
@@ -439,8 +443,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                          (int)(np + 1), st);
                 }));
             }
-            CK(cudaMemcpyAsync(ctx->h_counters, d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+            CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));                              // sync B
+            memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
             nchunks = ctx->h_counters[C_POOL] >> POOL_BITS;            // packed: chunks above bit 40, pairs below
             ctx->h_counters[C_POOL] &= (1ull << POOL_BITS) - 1ull;
             if (ctx->h_counters[C_POOL] <= pool_cap && nchunks <= chunk_cap) break;
@@ -573,8 +579,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
                                                          ctx->seed, rng_base, pp, ctx->valid.as<uint8_t>(), d_counters);
     CK(cudaGetLastError()); ctx->n_launches++;
-    CK(cudaMemcpyAsync(ctx->h_counters, d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));                                      // sync C
+    memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
     const int64_t norph = (int64_t)ctx->h_counters[C_NORPH];
     const int64_t npre = np + norph;
     const int64_t ninvalid = (int64_t)ctx->h_counters[C_INVALID];
@@ -729,7 +737,8 @@ hem_ctx* hem_create(int device, uint64_t seed)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_ctl, sizeof(Ctl)) != cudaSuccess) {
+        cudaHostAlloc((void**)&ctx->h_ctl, sizeof(Ctl), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->h_ctl_dev, ctx->h_ctl, 0) != cudaSuccess) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
         return nullptr;
@@ -749,7 +758,7 @@ void hem_destroy(hem_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (Level& L : ctx->levels) { release(L.geo); release(L.sh); }
+    for (Level& L : ctx->levels) { release(L.geo); release(L.sh); release(L.ex_xyz); release(L.ex_col); release(L.ex_op); release(L.ex_cov); }
     DevBuf* all[] = { &ctx->in_xyz, &ctx->in_col, &ctx->in_op, &ctx->in_cov, &ctx->in_sh, &ctx->in_w, &ctx->in_mask,
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
@@ -855,9 +864,38 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
         if (lv < ctx->binds.size() && ctx->binds[lv].set) {
             const hem_ctx::OutBind& B = ctx->binds[lv];
             if (B.cap < ctx->levels[lv].n) { bind_too_small = true; continue; }
-            CK(cudaEventRecord(ctx->ev_level, st));
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_level, 0));
-            CKR(export_level(ctx, (int)lv, B.xyz, B.color, B.opacity, B.cov6, B.sh, nullptr, nullptr, ctx->copy_stream));
+            // The de-interleave kernel runs on the MAIN stream (the persistent gate / moment kernels of the
+            // next level would starve it on the copy stream); the copy stream then carries DMA only.
+            Level& LV = ctx->levels[lv];
+            const int64_t m = LV.n;
+            if (m > 0) {
+                const bool hx = B.xyz && !is_device_ptr(B.xyz), hc = B.color && !is_device_ptr(B.color);
+                const bool ho = B.opacity && !is_device_ptr(B.opacity), hv = B.cov6 && !is_device_ptr(B.cov6);
+                if (hx) CKR(ensure(ctx, LV.ex_xyz, (size_t)m * 12));
+                if (hc) CKR(ensure(ctx, LV.ex_col, (size_t)m * 12));
+                if (ho) CKR(ensure(ctx, LV.ex_op, (size_t)m * 4));
+                if (hv) CKR(ensure(ctx, LV.ex_cov, (size_t)m * 24));
+                float* dx = B.xyz ? (hx ? LV.ex_xyz.as<float>() : B.xyz) : nullptr;
+                float* dc = B.color ? (hc ? LV.ex_col.as<float>() : B.color) : nullptr;
+                float* dop = B.opacity ? (ho ? LV.ex_op.as<float>() : B.opacity) : nullptr;
+                float* dcv = B.cov6 ? (hv ? LV.ex_cov.as<float>() : B.cov6) : nullptr;
+                if (dx || dc || dop || dcv) {
+                    k_export<<<blocks_for(m, 256), 256, 0, st>>>(LV.geo.as<float4>(), m, dx, dc, dop, dcv, nullptr, nullptr);
+                    CK(cudaGetLastError()); ctx->n_launches++;
+                }
+                CK(cudaEventRecord(ctx->ev_level, st));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_level, 0));
+                cudaStream_t cs = ctx->copy_stream;
+                if (B.sh && ctx->F > 0) {
+                    const bool to_dev = is_device_ptr(B.sh);
+                    CK(cudaMemcpyAsync(B.sh, LV.shp, (size_t)m * ctx->F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
+                    if (!to_dev) ctx->bytes_d2h += (size_t)m * ctx->F * 4;
+                }
+                if (hv) { CK(cudaMemcpyAsync(B.cov6, dcv, (size_t)m * 24, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 24; }
+                if (hx) { CK(cudaMemcpyAsync(B.xyz, dx, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
+                if (hc) { CK(cudaMemcpyAsync(B.color, dc, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
+                if (ho) { CK(cudaMemcpyAsync(B.opacity, dop, (size_t)m * 4, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 4; }
+            }
         }
     }
     if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }

@@ -55,6 +55,22 @@ struct Ctl {
     double sum_radius;
 };
 
+// Control block -> mapped pinned host memory.  The host reads step sizes after a stream sync; a DMA
+// readback would queue behind the bulk level downloads that share the D2H copy engine.
+__global__ void k_publish(const Ctl* __restrict__ d, Ctl* __restrict__ h_mapped)
+{
+    const unsigned* s = reinterpret_cast<const unsigned*>(d);
+    unsigned* o = reinterpret_cast<unsigned*>(h_mapped);
+    for (unsigned i = threadIdx.x; i < sizeof(Ctl) / 4; i += blockDim.x) o[i] = s[i];
+}
+
+// zero-fill by a kernel (a cudaMemsetAsync may be routed through a copy engine and queue behind bulk DMA)
+__global__ void k_zero(uint4* __restrict__ p, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __device__ __forceinline__ int f2ord(float f)
 {
     int i = __float_as_int(f);
