@@ -63,6 +63,13 @@ struct hem_ctx {
     std::string err;
     bool timing = false, keep_pairs = false, smd_prefilter = true;
     int sumlw_mode = 0;            // 0 auto, 1 radix sort, 2 claim table
+    // prep of the next level carried over from k_finish (no prep kernel, no host sync)
+    bool prep_valid = false;
+    int prep_level = -1;
+    int64_t prep_n = 0;
+    Ctl prep_stats;
+    bool dense_hint = false;       // last step had more than 4 accepted pairs per component
+    size_t pool_min = 0;           // pair pool size learned from an overflow
     double cell_scale = 0.5;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
@@ -77,7 +84,8 @@ struct hem_ctx {
     // workspace (grow-only, reused across steps and builds)
     DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
-    DevBuf radius, psafe, pflag, prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
+    DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
+    DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
     DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf;
     unsigned long long* h_counters = nullptr;   // pinned
@@ -296,22 +304,39 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     uint32_t* d_pair_cnt = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt);
     float* d_sumlw = (float*)((char*)ctx->ctlbuf.p + off_sumlw);
     uint32_t* d_cnt_c = (uint32_t*)((char*)ctx->ctlbuf.p + off_cntc);
-    CKR(ensure(ctx, ctx->radius, n * 4));
-    CKR(ensure(ctx, ctx->psafe, n));
-    CKR(ensure(ctx, ctx->pflag, n * 4));
+    const int set = l & 1;
+    DevBuf& RAD = set ? ctx->radius2 : ctx->radius;
+    DevBuf& SAFE = set ? ctx->psafe2 : ctx->psafe;
+    DevBuf& PFLAG = set ? ctx->pflag2 : ctx->pflag;
+    DevBuf& RAD_N = set ? ctx->radius : ctx->radius2;
+    DevBuf& SAFE_N = set ? ctx->psafe : ctx->psafe2;
+    DevBuf& PFLAG_N = set ? ctx->pflag : ctx->pflag2;
+    const bool carried = ctx->prep_valid && ctx->prep_level == l && ctx->prep_n == n;
+    if (!carried) {
+        CKR(ensure(ctx, RAD, n * 4));
+        CKR(ensure(ctx, SAFE, n));
+        CKR(ensure(ctx, PFLAG, n * 4));
+    }
     CKR(ensure(ctx, ctx->prank, n * 4));
     k_zero<<<(unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
     CK(cudaGetLastError()); ctx->n_launches++;
-    k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
-        geo, n, distance_delta, ctx->radius.as<float>(), ctx->pflag.as<uint32_t>(), ctx->psafe.as<uint8_t>(), d_ctl);
-    CK(cudaGetLastError()); ctx->n_launches++;
+    Ctl ps;
+    if (carried) {
+        // radii, flags, certificates and statistics of this level were produced by the previous step's k_finish
+        ps = ctx->prep_stats;
+    } else {
+        k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
+            geo, n, distance_delta, RAD.as<float>(), PFLAG.as<uint32_t>(), SAFE.as<uint8_t>(), d_ctl);
+        CK(cudaGetLastError()); ctx->n_launches++;
+        k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));                                  // sync A (level 0 / after an erasing filter only)
+        ps = *ctx->h_ctl;
+    }
+    ctx->prep_valid = false;
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
-        return cub::DeviceScan::ExclusiveSum(t, b, ctx->pflag.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
+        return cub::DeviceScan::ExclusiveSum(t, b, PFLAG.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
     }));
-    k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));                                      // sync A
-    const Ctl ps = *ctx->h_ctl;
     const int64_t np = (int64_t)ps.n_parents;
     S.n_parents = np;
     S.n_certified = (int64_t)ps.n_certified;
@@ -326,8 +351,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CKR(ensure(ctx, out.sh, (size_t)cap_rows * std::max(Fp, 1) * 4));
     out.shp = out.sh.as<float>();
     CKR(ensure(ctx, ctx->valid, cap_rows));
+    CKR(ensure(ctx, RAD_N, cap_rows * 4));
+    CKR(ensure(ctx, SAFE_N, cap_rows));
+    CKR(ensure(ctx, PFLAG_N, cap_rows * 4));
 
     int64_t P = 0;
+    size_t pool_cap_used = 0, chunk_cap_final = 0;
     const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
     if (have_pairs) {
         // ---- S2 grid --------------------------------------------------------------------------
@@ -340,7 +369,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 if (!std::isfinite(bmin[a])) bmin[a] = -FLT_MAX;
                 if (!std::isfinite(bmax[a])) bmax[a] = FLT_MAX;
             }
-            double h = ps.n_radius ? ctx->cell_scale * (ps.sum_radius / (double)ps.n_radius) : 1.0;
+            double h = ps.n_radius ? ctx->cell_scale * ((double)ps.sum_radius_fx / 65536.0 / (double)ps.n_radius) : 1.0;
             if (!(h > 0)) h = 1.0;
             const double max_cells = 1 << 24;
             double ext[3];
@@ -403,13 +432,20 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
         k_ptab<<<blocks_for(np, 256), 256, 0, st>>>(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     ctx->radius.as<float>(), ctx->psafe.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
+                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
-        size_t pool_cap = std::max<size_t>(ctx->pool.cap / 8, std::max<size_t>((size_t)8 * n / G, 1 << 16));
+        size_t pool_cap = std::max<size_t>(std::max<size_t>(ctx->pool.cap / 8, ctx->pool_min), std::max<size_t>((size_t)8 * n / G, 1 << 16));
         unsigned long long nchunks = 0;
+        // Single GPU, claim-table regime: nothing between the gate and the end of the step needs a size on
+        // the host (launches are sized by capacities, counts are read on the device), so the step runs with
+        // ONE host sync at its end; a pool overflow is detected there and the step is redone with a larger pool.
+        const bool guess_claims = ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && !ctx->dense_hint);
+        const bool fast = (G == 1) && !ctx->keep_pairs && guess_claims;
+        size_t chunk_cap_used = 0;
         for (int attempt = 0; attempt < 8; ++attempt) {
             const size_t chunk_cap = (size_t)my_np + pool_cap / (GATE_OUTCAP - 32) + 16;
+            chunk_cap_used = chunk_cap;
             CKR(ensure(ctx, ctx->pool, pool_cap * 8));
             CKR(ensure(ctx, ctx->chunks, chunk_cap * 16));
             if (attempt > 0) {      // pool overflow retry: reopen the counters and the counts
@@ -443,6 +479,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                          (int)(np + 1), st);
                 }));
             }
+            if (fast) break;
             k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));                              // sync B
@@ -453,8 +490,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             pool_cap = (size_t)ctx->h_counters[C_POOL] + (size_t)ctx->h_counters[C_POOL] / 4 + 1024;
             if (attempt == 7) { ctx->err = "pair pool overflow persisted"; return HEM_ERR_STATE; }
         }
+        pool_cap_used = pool_cap; chunk_cap_final = chunk_cap_used;
         std::vector<int64_t> pb(G + 1, 0);          // pair offsets at the slab bounds
-        if (G == 1) {
+        if (fast) {
+            pb[1] = (int64_t)pool_cap;              // capacity; the true count is read on the device / at the final sync
+        } else if (G == 1) {
             pb[1] = (int64_t)ctx->h_counters[C_POOL];
         } else {
             // exchange the per-parent counts, scan them everywhere, fetch the offsets at the slab bounds
@@ -469,24 +509,26 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CK(cudaStreamSynchronize(st));                              // sync B2 (multi-GPU only)
             for (int q = 0; q <= G; ++q) pb[q] = hb[q];
         }
-        P = pb[G];
+        P = pb[G];                                  // fast flow: an upper bound (capacity) until the final sync
         if (P >= (int64_t)1 << 32) { ctx->err = "more than 2^32-1 accepted pairs per level is not supported"; return HEM_ERR_INVALID; }
         S.n_pairs = P;
         CKR(ensure(ctx, ctx->csr_s, std::max<int64_t>(P, 1) * 8));
         CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
         CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
-        if (nchunks > 0) {
-            k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
-                ctx->chunks.as<uint4>(), nchunks, ctx->pool.as<uint2>(), ctx->pair_off_s.as<uint32_t>(), ctx->csr_s.as<uint2>());
+        if (fast || nchunks > 0) {
+            const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
+            k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
+                ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
+                ctx->pair_off_s.as<uint32_t>(), ctx->csr_s.as<uint2>());
             CK(cudaGetLastError()); ctx->n_launches++;
         }
-        CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
+        if (G > 1) CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
         // sparse regime (the benchmark's): claim table, 2 launches; dense regime: stable radix sort of the
         // canonical CSR by child.  Both add a child's claims in ascending parent rank (bit-identical).
-        const bool use_claims = ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
+        const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
         const bool need_canon = !use_claims || ctx->keep_pairs;
         if (need_canon) {
             if (G > 1) {    // sharded: counts arrive in cell order, put them in canonical order here
@@ -511,7 +553,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                                 ctx->ovf.as<uint4>(), (unsigned long long)P, d_counters);
             CK(cudaGetLastError()); ctx->n_launches++;
             k_sumlw_claims<<<blocks_for(n, 256), 256, 0, st>>>(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
-                                                                n, d_sumlw);
+                                                                ctx->sumlw_mode == 2 ? ~0ull : 4096ull, n, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         } else if (P > 0) {
             CKR(ensure(ctx, ctx->sk, P * 4));
@@ -577,12 +619,32 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
     k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
-                                                         ctx->seed, rng_base, pp, ctx->valid.as<uint8_t>(), d_counters);
+                                                         ctx->seed, rng_base, pp, distance_delta, ctx->valid.as<uint8_t>(),
+                                                         RAD_N.as<float>(), SAFE_N.as<uint8_t>(), PFLAG_N.as<uint32_t>(), d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
     k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));                                      // sync C
     memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
+    if (have_pairs) {
+        // fast flow: the pair / chunk counts arrive only now (in the other flows this re-reads known values)
+        const unsigned long long packed = ctx->h_counters[C_POOL];
+        const unsigned long long pairs = packed & ((1ull << POOL_BITS) - 1ull), nch = packed >> POOL_BITS;
+        const bool overflow = pairs > pool_cap_used || nch > chunk_cap_final;
+        const bool claims_failed = ctx->h_counters[C_FAIL] != 0;
+        if (overflow || claims_failed) {
+            // nothing was corrupted (pool writes are guarded, the claim summation bailed out): redo the step
+            // with a larger pool / through the sort path; the carried prep of THIS level is still intact
+            if (overflow) ctx->pool_min = (size_t)pairs + (size_t)pairs / 4 + 1024;
+            if (claims_failed) ctx->dense_hint = true;
+            ctx->prep_valid = carried;
+            ctx->prep_level = l; ctx->prep_n = n; ctx->prep_stats = ps;
+            return run_step(ctx, l, hem_reduction, distance_delta, color_delta, decay_rate, rng_base);
+        }
+        P = (int64_t)pairs;
+        S.n_pairs = P;
+    }
+    ctx->dense_hint = P > 4 * n;
     const int64_t norph = (int64_t)ctx->h_counters[C_NORPH];
     const int64_t npre = np + norph;
     const int64_t ninvalid = (int64_t)ctx->h_counters[C_INVALID];
@@ -610,6 +672,18 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         out.n = nout;
     }
     S.n_out = out.n;
+    // hand the next level its prep (invalid as soon as the filter erased rows: positions shifted)
+    ctx->prep_valid = (ninvalid == 0);
+    ctx->prep_level = l + 1;
+    ctx->prep_n = npre;
+    ctx->prep_stats = Ctl();
+    {
+        const Ctl& hc = *ctx->h_ctl;
+        Ctl& nx = ctx->prep_stats;
+        for (int a = 0; a < 3; ++a) { nx.bbmax_u[a] = hc.nx_bbmax_u[a]; nx.bbmin_c[a] = hc.nx_bbmin_c[a]; }
+        nx.max_radius_bits = hc.nx_max_radius_bits; nx.n_radius = hc.nx_n_radius; nx.n_parents = hc.nx_n_parents;
+        nx.n_certified = hc.nx_n_certified; nx.sum_radius_fx = hc.nx_sum_radius_fx;
+    }
     if (ctx->timing) {
         CK(cudaEventRecord(ctx->ev[EV_END], st));
         CK(cudaEventSynchronize(ctx->ev[EV_END]));
@@ -634,8 +708,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CK(cudaMemcpyAsync(K.sumlw.data(), d_sumlw, n * 4, cudaMemcpyDeviceToHost, st));
         std::vector<uint32_t> pflag(n);
         std::vector<float> rad(n);
-        CK(cudaMemcpyAsync(pflag.data(), ctx->pflag.p, n * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(rad.data(), ctx->radius.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pflag.data(), PFLAG.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rad.data(), RAD.p, n * 4, cudaMemcpyDeviceToHost, st));
         std::vector<uint32_t> off32(np + 1, 0);
         K.child.resize(P);
         K.wl.resize(P);
@@ -761,7 +835,7 @@ void hem_destroy(hem_ctx* ctx)
     for (Level& L : ctx->levels) { release(L.geo); release(L.sh); release(L.ex_xyz); release(L.ex_col); release(L.ex_op); release(L.ex_cov); }
     DevBuf* all[] = { &ctx->in_xyz, &ctx->in_col, &ctx->in_op, &ctx->in_cov, &ctx->in_sh, &ctx->in_w, &ctx->in_mask,
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
-                      &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
+                      &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->radius2, &ctx->psafe2, &ctx->pflag2, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
@@ -819,6 +893,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     ctx->stats.assign(cluster_level, StepStats());
     ctx->pairs.assign(ctx->keep_pairs ? cluster_level : 0, StepPairs());
 
+    ctx->prep_valid = false;
     // level 0 = the input (Mixture::initMixture, mixture.cpp:287-333)
     Level& L0 = ctx->levels[0];
     L0.n = n;

@@ -40,7 +40,7 @@ struct GridP {
 
 // Per-step control block.  Everything in it (and the per-parent / per-child arrays that follow
 // it in the same allocation) starts from zero, so ONE memset opens a step.
-enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_WORK = 4, C_WORK2 = 5, C_OVF = 6, C_COUNT = 8 };
+enum { C_POOL = 0, C_CHUNK = 1, C_INVALID = 2, C_NORPH = 3, C_WORK = 4, C_WORK2 = 5, C_OVF = 6, C_FAIL = 7, C_COUNT = 8 };
 
 struct Ctl {
     unsigned long long counters[C_COUNT];
@@ -52,7 +52,14 @@ struct Ctl {
     unsigned int n_radius;          // parents with finite positive radius
     unsigned int n_parents;
     unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
-    double sum_radius;
+    unsigned long long sum_radius_fx;   // sum of min(radius, 65536) in 2^-16 units: integer adds are order-independent,
+                                        // so the grid cell size (and with it every summation order) is deterministic
+    // the same statistics for the NEXT level, produced by k_finish while it finalises the output rows
+    // (so the next step starts without a prep kernel and without a host sync)
+    unsigned int nx_bbmax_u[3];
+    unsigned int nx_bbmin_c[3];
+    unsigned int nx_max_radius_bits, nx_n_radius, nx_n_parents, nx_n_certified;
+    unsigned long long nx_sum_radius_fx;
 };
 
 // Control block -> mapped pinned host memory.  The host reads step sizes after a stream sync; a DMA
@@ -70,6 +77,8 @@ __global__ void k_zero(uint4* __restrict__ p, size_t n16)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
         p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
+
+__device__ __forceinline__ unsigned long long radius_fx(float r) { return (unsigned long long)(fminf(r, 65536.0f) * 65536.0f); }
 
 __device__ __forceinline__ int f2ord(float f)
 {
@@ -154,12 +163,12 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     __shared__ uint8_t s_safe[256];
     __shared__ int s_woff[9];
     __shared__ int s_red[8][8];
-    __shared__ double s_redd[8];
+    __shared__ unsigned long long s_redd[8];
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
     unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0;
-    double rsum = 0.0;
+    unsigned long long rsum = 0ull;
     const int64_t ntiles = (n + 255) / 256;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t i = tile * 256 + tid;
@@ -197,7 +206,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
             const Sym3 c = { s_cov[tid][0], s_cov[tid][1], s_cov[tid][2], s_cov[tid][3], s_cov[tid][4], s_cov[tid][5] };
             double emin, emax;
             const float rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(c, &emin, &emax)));       // mixture.cpp:88
-            if (rad > 0.0f && rad < FLT_MAX) { rbits = max(rbits, __float_as_uint(rad)); rcount += 1; rsum += (double)rad; }
+            if (rad > 0.0f && rad < FLT_MAX) { rbits = max(rbits, __float_as_uint(rad)); rcount += 1; rsum += radius_fx(rad); }
             s_rad[s_src[tid]] = rad;
             const bool cert = parent_cov_certified(c, det_sym3(c), emin, emax);
             s_safe[s_src[tid]] = cert ? 1 : 0;
@@ -238,7 +247,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
         if (rcount) {
             atomicMax(&ctl->max_radius_bits, rbits);
             atomicAdd(&ctl->n_radius, rcount);
-            atomicAdd(&ctl->sum_radius, rsum);
+            atomicAdd(&ctl->sum_radius_fx, rsum);
         }
     }
 }
@@ -597,12 +606,14 @@ k_gate(GateArgs A)
 
 // pool -> cell-order CSR (what the moment kernel streams; a rank's slab of parents owns one
 // contiguous segment of it, which is what the ranks exchange)
-__global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long long nchunks,
-                             const uint2* __restrict__ pool, const uint32_t* __restrict__ pair_off_s,
-                             uint2* __restrict__ csr_s)
+__global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned long long* __restrict__ counters,
+                             unsigned long long chunk_cap, const uint2* __restrict__ pool,
+                             const uint32_t* __restrict__ pair_off_s, uint2* __restrict__ csr_s)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // launched over the chunk capacity; the number of chunks written is read on the device
+    const unsigned long long nchunks = min(counters[C_POOL] >> POOL_BITS, chunk_cap);
     if (c >= nchunks) return;
     const uint4 ch = chunks[c];
     const size_t dst = (size_t)pair_off_s[ch.x] + ch.w;
@@ -668,8 +679,8 @@ __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restr
 }
 
 __global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ claims,
-                               const uint4* __restrict__ ovf, const unsigned long long* __restrict__ counters,
-                               int64_t n, float* __restrict__ sumlw)
+                               const uint4* __restrict__ ovf, unsigned long long* __restrict__ counters,
+                               unsigned long long ovf_limit, int64_t n, float* __restrict__ sumlw)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -695,6 +706,10 @@ __global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* 
     }
     const uint32_t mt = min(m, (uint32_t)CLAIM_K);
     const unsigned long long nov = (m > (uint32_t)CLAIM_K) ? counters[C_OVF] : 0ull;
+    if (nov > ovf_limit) {          // dense regime reached the claim table: give up, the host redoes the step by sorting
+        counters[C_FAIL] = 1ull;
+        return;
+    }
     float s = 0.0f;
     long long last = -1;
     for (uint32_t i = 0; i < m; ++i) {                   // selection by ascending parent rank
@@ -907,34 +922,88 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
 // covariance, fresh parent flag drawn at the pre-filter position (mixture.cpp:257-259) and the
 // validity predicate (mixture.cpp:262-270).  One THREAD per row: the Philox rounds and the
 // determinant used to run warp-uniformly once per parent inside the moment kernel.
-__global__ void k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
-                         const float* __restrict__ sumlw, int64_t n_in, uint64_t seed, uint64_t rng_base,
-                         float pp, uint8_t* __restrict__ valid, unsigned long long* __restrict__ counters)
+__global__ void __launch_bounds__(256)
+k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ orank,
+         const float* __restrict__ sumlw, int64_t n_in, uint64_t seed, uint64_t rng_base,
+         float pp, float distance_delta, uint8_t* __restrict__ valid,
+         float* __restrict__ radius_n, uint8_t* __restrict__ psafe_n, uint32_t* __restrict__ pflag_n,
+         Ctl* __restrict__ ctl)
 {
+    __shared__ unsigned int s_red[8][10];
+    __shared__ unsigned long long s_redd[8];
     // pre-filter row count = parents + orphans, read on the device (the host learns it afterwards)
     const int64_t norph = (int64_t)orank[n_in - 1] + (sumlw[n_in - 1] == 0.0f ? 1 : 0);
     const int64_t n = np + norph;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) counters[C_NORPH] = (unsigned long long)norph;
+    if (j == 0) ctl->counters[C_NORPH] = (unsigned long long)norph;
     bool bad = false;
+    unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
+    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0;
+    unsigned long long rsum = 0ull;
     if (j < n) {
         const float4 q0 = geo[4 * j], q1 = geo[4 * j + 1];
         float4 q2 = geo[4 * j + 2];
         float dt = q2.w;
+        const Sym3 cc = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
         if (j < np) {               // merged row: determinant in the reference's operation order
-            const Sym3 c = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
-            dt = det_sym3(c);
+            dt = det_sym3(cc);
             q2.w = dt;
             geo[4 * j + 2] = q2;
         }
-        const Sym3 cc = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
-        reinterpret_cast<float*>(geo)[16 * j + 15] = __uint_as_float(
-            (parent_flag(seed, rng_base + (uint64_t)j, pp) ? 1u : 0u) | (child_cov_certified(cc, dt) ? 2u : 0u));
+        const bool flag = parent_flag(seed, rng_base + (uint64_t)j, pp);
+        reinterpret_cast<float*>(geo)[16 * j + 15] =
+            __uint_as_float((flag ? 1u : 0u) | (child_cov_certified(cc, dt) ? 2u : 0u));
         bad = (q0.x != q0.x || q0.y != q0.y || q0.z != q0.z) || (dt != dt) || dt <= 0.0f;
         valid[j] = bad ? 0 : 1;
+        // next level's S1 (mixture.cpp:70-95), valid as long as nothing gets erased by the filter
+        float rad = 0.0f;
+        bool cert = false;
+        if (flag) {
+            double emin, emax;
+            rad = fm(distance_delta, __fsqrt_rn(eig_max_sym3(cc, &emin, &emax)));
+            cert = parent_cov_certified(cc, dt, emin, emax);
+            if (rad > 0.0f && rad < FLT_MAX) { rbits = __float_as_uint(rad); rcount = 1; rsum = radius_fx(rad); }
+            pcount = 1; ccount = cert ? 1u : 0u;
+        }
+        radius_n[j] = rad; psafe_n[j] = cert ? 1 : 0; pflag_n[j] = flag ? 1u : 0u;
+        if (q0.x == q0.x) { const unsigned o = f2u(q0.x); bmax[0] = o; bminc[0] = ~o; }
+        if (q0.y == q0.y) { const unsigned o = f2u(q0.y); bmax[1] = o; bminc[1] = ~o; }
+        if (q0.z == q0.z) { const unsigned o = f2u(q0.z); bmax[2] = o; bminc[2] = ~o; }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[C_INVALID], (unsigned long long)__popc(m));
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(full, bad);
+    if (lane == 0 && m) atomicAdd(&ctl->counters[C_INVALID], (unsigned long long)__popc(m));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { bmax[a] = __reduce_max_sync(full, bmax[a]); bminc[a] = __reduce_max_sync(full, bminc[a]); }
+    rbits = __reduce_max_sync(full, rbits);
+    rcount = __reduce_add_sync(full, rcount); pcount = __reduce_add_sync(full, pcount); ccount = __reduce_add_sync(full, ccount);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
+    if (lane == 0) {
+        for (int a = 0; a < 3; ++a) { s_red[warp][a] = bminc[a]; s_red[warp][3 + a] = bmax[a]; }
+        s_red[warp][6] = rbits; s_red[warp][7] = rcount; s_red[warp][8] = pcount; s_red[warp][9] = ccount;
+        s_redd[warp] = rsum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            for (int a = 0; a < 3; ++a) { bminc[a] = max(bminc[a], s_red[w][a]); bmax[a] = max(bmax[a], s_red[w][3 + a]); }
+            rbits = max(rbits, s_red[w][6]); rcount += s_red[w][7]; pcount += s_red[w][8]; ccount += s_red[w][9];
+            rsum += s_redd[w];
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (bmax[a]) atomicMax(&ctl->nx_bbmax_u[a], bmax[a]);
+            if (bminc[a]) atomicMax(&ctl->nx_bbmin_c[a], bminc[a]);
+        }
+        if (pcount) atomicAdd(&ctl->nx_n_parents, pcount);
+        if (ccount) atomicAdd(&ctl->nx_n_certified, ccount);
+        if (rcount) {
+            atomicMax(&ctl->nx_max_radius_bits, rbits);
+            atomicAdd(&ctl->nx_n_radius, rcount);
+            atomicAdd(&ctl->nx_sum_radius_fx, rsum);
+        }
+    }
 }
 
 // staged merged rows (index = cell-order position t) -> their final place (index = canonical rank)
