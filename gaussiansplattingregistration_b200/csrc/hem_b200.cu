@@ -70,6 +70,7 @@ struct hem_ctx {
     Ctl prep_stats;
     bool dense_hint = false;       // last step had more than 4 accepted pairs per component
     size_t pool_min = 0;           // pair pool size learned from an overflow
+    int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
     double cell_scale = 0.5;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
@@ -86,7 +87,7 @@ struct hem_ctx {
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
     DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
-    DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
+    DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
     DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
@@ -201,6 +202,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -227,10 +229,11 @@ bool nccl_load()
     g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
     g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
     g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
     g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
     g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Broadcast || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         g_nccl.err = "libnccl lacks a required symbol";
         g_nccl.lib = nullptr;
         return false;
@@ -249,21 +252,17 @@ bool nccl_load()
     } while (0)
 
 // slab bounds: parents (in cell order) [bounds[r], bounds[r+1]) belong to rank r
-inline int64_t slab_bound(int64_t np, int r, int world) { return np * (int64_t)r / world; }
+// equal chunks of ceil(np/G) parents (the last ranks may own fewer): equal counts let the exchanges be single
+// in-place ncclAllGather calls instead of G broadcasts
+inline int64_t slab_chunk(int64_t np, int world) { return (np + world - 1) / world; }
+inline int64_t slab_bound(int64_t np, int r, int world) { return std::min<int64_t>(slab_chunk(np, world) * r, np); }
 
-// every rank owns the byte range [bounds[r]*elem, bounds[r+1]*elem) of `buf`; after the call all
-// ranks hold all ranges (grouped in-place broadcasts = an all-gather with uneven counts)
-int allgather_ranges(hem_ctx* ctx, void* buf, size_t elem, const int64_t* bounds)
+// in-place all-gather: rank r owns elements [r*chunk, (r+1)*chunk) of `buf` (G*chunk elements long)
+int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk)
 {
-    if (ctx->world <= 1) return HEM_OK;
-    NK(g_nccl.GroupStart());
-    for (int q = 0; q < ctx->world; ++q) {
-        const size_t cnt = (size_t)(bounds[q + 1] - bounds[q]) * elem;
-        if (cnt == 0) continue;
-        char* ptr = (char*)buf + (size_t)bounds[q] * elem;
-        NK(g_nccl.Broadcast(ptr, ptr, cnt, /*ncclChar*/ 0, q, ctx->nccl_comm, ctx->stream));
-    }
-    NK(g_nccl.GroupEnd());
+    if (ctx->world <= 1 || chunk <= 0) return HEM_OK;
+    const size_t bytes = (size_t)chunk * elem;
+    NK(g_nccl.AllGather((char*)buf + (size_t)ctx->rank * bytes, buf, bytes, /*ncclChar*/ 0, ctx->nccl_comm, ctx->stream));
     return HEM_OK;
 }
 
@@ -293,7 +292,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     // ---- S1 prep --------------------------------------------------------------------------
     // control block + the arrays that must start from zero live in one allocation: one memset per step
     //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) | cnt_c (n) ]
-    const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
+    const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1 + 64) * 4 + 255) / 256 * 256;   // +64: all-gather padding
     const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
     const size_t off_cntc = off_sumlw + ((size_t)n * 4 + 255) / 256 * 256;
     const size_t ctl_bytes = (off_cntc + (size_t)n * 4 + 15) / 16 * 16;
@@ -422,7 +421,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
-        const int G = ctx->world, R = ctx->rank;
+        // levels below shard_min_n are not worth an exchange: every rank builds them whole (identical results)
+        const int G = (ctx->world > 1 && n >= ctx->shard_min_n) ? ctx->world : 1;
+        const int R = G > 1 ? ctx->rank : 0;
         std::vector<int64_t> tb(G + 1);
         for (int q = 0; q <= G; ++q) tb[q] = slab_bound(np, q, G);
         const int64_t my_np = tb[R + 1] - tb[R];
@@ -498,7 +499,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             pb[1] = (int64_t)ctx->h_counters[C_POOL];
         } else {
             // exchange the per-parent counts, scan them everywhere, fetch the offsets at the slab bounds
-            CKR(allgather_ranges(ctx, d_pair_cnt_s, 4, tb.data()));
+            CKR(allgather_equal(ctx, d_pair_cnt_s, 4, slab_chunk(np, G)));
             CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
                 return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt_s, ctx->pair_off_s.as<uint32_t>(),
                                                      (int)(np + 1), st);
@@ -515,14 +516,32 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->csr_s, std::max<int64_t>(P, 1) * 8));
         CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
         CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
-        if (fast || nchunks > 0) {
-            const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
-            k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
-                ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
-                ctx->pair_off_s.as<uint32_t>(), ctx->csr_s.as<uint2>());
-            CK(cudaGetLastError()); ctx->n_launches++;
+        if (G == 1) {
+            if (fast || nchunks > 0) {
+                const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
+                k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
+                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
+                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>());
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
+        } else {
+            // every rank gets every slab's pairs: segments padded to the longest one, ONE in-place all-gather,
+            // then unpacked into the contiguous cell-order CSR
+            int64_t M = 0;
+            for (int q = 0; q < G; ++q) M = std::max(M, pb[q + 1] - pb[q]);
+            CKR(ensure(ctx, ctx->csr_pad, (size_t)std::max<int64_t>(M, 1) * G * 8));
+            if (nchunks > 0) {
+                k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
+                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
+                    ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>());
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
+            CKR(allgather_equal(ctx, ctx->csr_pad.p, 8, M));
+            for (int q = 0; q < G; ++q)
+                if (pb[q + 1] > pb[q])
+                    CK(cudaMemcpyAsync(ctx->csr_s.as<uint2>() + pb[q], ctx->csr_pad.as<uint2>() + (size_t)q * M,
+                                       (size_t)(pb[q + 1] - pb[q]) * 8, cudaMemcpyDeviceToDevice, st));
         }
-        if (G > 1) CKR(allgather_ranges(ctx, ctx->csr_s.p, 8, pb.data()));       // every rank gets every slab's pairs
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
@@ -577,8 +596,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
-            CKR(ensure(ctx, ctx->stage_geo, (size_t)np * 64));
-            CKR(ensure(ctx, ctx->stage_sh, (size_t)np * std::max(Fp, 1) * 4));
+            CKR(ensure(ctx, ctx->stage_geo, (size_t)slab_chunk(np, G) * G * 64));
+            CKR(ensure(ctx, ctx->stage_sh, (size_t)slab_chunk(np, G) * G * std::max(Fp, 1) * 4));
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
         if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
@@ -592,8 +611,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (G > 1) {
             // all-gather the merged rows (staged in cell order, one contiguous range per rank), then put
             // them at their canonical place: every rank ends the step with the complete next level
-            CKR(allgather_ranges(ctx, ctx->stage_geo.p, 64, tb.data()));
-            if (Fp > 0) CKR(allgather_ranges(ctx, ctx->stage_sh.p, (size_t)Fp * 4, tb.data()));
+            CKR(allgather_equal(ctx, ctx->stage_geo.p, 64, slab_chunk(np, G)));
+            if (Fp > 0) CKR(allgather_equal(ctx, ctx->stage_sh.p, (size_t)Fp * 4, slab_chunk(np, G)));
             k_permute_rows<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), (int)np, ctx->stage_geo.as<float4>(),
                                                                       ctx->stage_sh.as<float>(), Fp, out.geo.as<float4>(),
                                                                       out.sh.as<float>());
@@ -837,7 +856,7 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->radius2, &ctx->psafe2, &ctx->pflag2, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
-                      &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
+                      &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
                       &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf };
     for (DevBuf* b : all) release(*b);
@@ -866,6 +885,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
+    else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
     else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }

@@ -608,7 +608,7 @@ k_gate(GateArgs A)
 // contiguous segment of it, which is what the ranks exchange)
 __global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned long long* __restrict__ counters,
                              unsigned long long chunk_cap, const uint2* __restrict__ pool,
-                             const uint32_t* __restrict__ pair_off_s, uint2* __restrict__ csr_s)
+                             const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -616,7 +616,7 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned lo
     const unsigned long long nchunks = min(counters[C_POOL] >> POOL_BITS, chunk_cap);
     if (c >= nchunks) return;
     const uint4 ch = chunks[c];
-    const size_t dst = (size_t)pair_off_s[ch.x] + ch.w;
+    const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
     for (uint32_t k = lane; k < ch.z; k += 32) csr_s[dst + k] = pool[(size_t)ch.y + k];
 }
 

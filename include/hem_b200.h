@@ -63,6 +63,8 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
  *   "sumlw_mode"  0 (default) auto, 1 stable radix sort by child, 2 claim table: two bit-identical
  *                 ways of adding a child's claims in ascending parent order
+ *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
+ *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
  *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
  *                 (the reference consumes one draw per level-0 component first,
  *                 src/cpp_ext/src/mixture.cpp:330, then one per pre-filter

@@ -34,7 +34,7 @@ def _worker(rank, world, port, ret):
         ok &= int(bounds[0, 0]) == 0 and int(bounds[-1, 1]) == n_parents
         ok &= bool((bounds[1:, 0] == bounds[:-1, 1]).all())                   # contiguous, no gap / overlap
         sizes = bounds[:, 1] - bounds[:, 0]
-        ok &= int(sizes.max() - sizes.min()) <= 1                              # balanced
+        ok &= int(sizes.max()) == -(-n_parents // world)                       # equal chunks of ceil(np/G)
     fake = bytes(np.random.default_rng(5).integers(0, 256, _capi.NCCL_ID_BYTES, dtype=np.uint8))
     got, r, w = exchange_unique_id(make_id=lambda: fake)
     ok &= got == fake and r == rank and w == world
@@ -55,7 +55,7 @@ def test_slab_range_rejects_bad_arguments():
     from gaussiansplattingregistration_b200._capi import HemError
     from gaussiansplattingregistration_b200.hem import slab_range
     assert slab_range(10, 0, 1) == (0, 10)
-    assert [slab_range(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    assert [slab_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     with pytest.raises(HemError):
         slab_range(10, 4, 4)
     with pytest.raises(HemError):

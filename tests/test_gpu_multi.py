@@ -34,6 +34,7 @@ def _worker(rank, world, port, ret):
     single.build(*c.arrays(), cluster_level=L)
     want = [single.level(l, True) for l in range(L + 1)]
     multi = HemContext(rank, seed=7)
+    multi.set_option("shard_min_n", 20000)        # shard levels 0 and 1 of this small cloud, build level 2 whole
     multi.init_distributed()
     multi.build(*c.arrays(), cluster_level=L)
     ok = True
