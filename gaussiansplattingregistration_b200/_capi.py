@@ -36,6 +36,7 @@ SIGNATURES = {
     "hem_level_size": (C.c_int64, [C.c_void_p, C.c_int]),
     "hem_level_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hem_level_registration_inputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hem_bind_output": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "hem_clear_outputs": (C.c_int, [C.c_void_p]),
     "hem_step_stats": (C.c_int, [C.c_void_p, C.c_int, _d]),

@@ -146,6 +146,68 @@ __global__ void k_export(const float4* __restrict__ geo, int64_t n, float* __res
 }
 
 // ---------------------------------------------------------------------------
+// "Next" row: what the reference builds on the host right after the HEM step
+// to feed Open3D (src/utils/point_cloud_converter.py:31-49): points as FP64, colours = sh2rgb(DC) =
+// 0.28209479177387814 * c + 0.5 in FP64 (src/utils/graphics_utils.py:72-73), covariances unpacked to
+// [N,3,3] FP64 (src/utils/general_utils.py:32-40), and — the reference's own TODO
+// (point_cloud_converter.py:44-47) — a normal from the covariance: the eigenvector of the smallest
+// eigenvalue (FP64 closed form + cross products), instead of a KD-tree estimate_normals pass.
+// ---------------------------------------------------------------------------
+__global__ void k_registration_inputs(const float4* __restrict__ geo, int64_t n, double* __restrict__ points,
+                                      double* __restrict__ colors, double* __restrict__ cov33,
+                                      double* __restrict__ normals)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q0 = geo[4 * i], q1 = geo[4 * i + 1], q2 = geo[4 * i + 2], q3 = geo[4 * i + 3];
+    if (points) { points[3 * i] = (double)q0.x; points[3 * i + 1] = (double)q0.y; points[3 * i + 2] = (double)q0.z; }
+    if (colors) {
+        colors[3 * i] = (double)q3.x * 0.28209479177387814 + 0.5;
+        colors[3 * i + 1] = (double)q3.y * 0.28209479177387814 + 0.5;
+        colors[3 * i + 2] = (double)q3.z * 0.28209479177387814 + 0.5;
+    }
+    const double a = q1.x, b = q1.y, c = q1.z, d = q1.w, e = q2.x, f = q2.y;   // [a b c; b d e; c e f]
+    if (cov33) {
+        double* o = cov33 + 9 * i;
+        o[0] = a; o[1] = b; o[2] = c; o[3] = b; o[4] = d; o[5] = e; o[6] = c; o[7] = e; o[8] = f;
+    }
+    if (normals) {
+        // smallest eigenvalue by the trigonometric closed form in FP64, eigenvector = the largest of the
+        // three cross products of rows of (A - lambda I)
+        const double m = (a + d + f) / 3.0;
+        const double k00 = a - m, k11 = d - m, k22 = f - m;
+        const double p2 = (k00 * k00 + k11 * k11 + k22 * k22 + 2.0 * (b * b + c * c + e * e)) / 6.0;
+        double nx = 0.0, ny = 0.0, nz = 1.0;
+        if (p2 > 0.0) {
+            const double pp = sqrt(p2);
+            const double det = (k00 * (k11 * k22 - e * e) - b * (b * k22 - e * c) + c * (b * e - k11 * c)) / (pp * pp * pp);
+            const double r = fmin(1.0, fmax(-1.0, 0.5 * det));
+            const double phi = acos(r) / 3.0;
+            const double lmin = m + 2.0 * pp * cos(phi + 2.0943951023931953);      // + 2*pi/3: the smallest root
+            const double r0x = a - lmin, r0y = b, r0z = c, r1x = b, r1y = d - lmin, r1z = e, r2x = c, r2y = e, r2z = f - lmin;
+            double cx[3] = { r0y * r1z - r0z * r1y, r0y * r2z - r0z * r2y, r1y * r2z - r1z * r2y };
+            double cy[3] = { r0z * r1x - r0x * r1z, r0z * r2x - r0x * r2z, r1z * r2x - r1x * r2z };
+            double cz[3] = { r0x * r1y - r0y * r1x, r0x * r2y - r0y * r2x, r1x * r2y - r1y * r2x };
+            int best = 0;
+            double bn = -1.0;
+            for (int k = 0; k < 3; ++k) {
+                const double nn = cx[k] * cx[k] + cy[k] * cy[k] + cz[k] * cz[k];
+                if (nn > bn) { bn = nn; best = k; }
+            }
+            if (bn > 0.0) {
+                const double inv = 1.0 / sqrt(bn);
+                nx = cx[best] * inv; ny = cy[best] * inv; nz = cz[best] * inv;
+                // sign convention: the largest-magnitude component is positive (deterministic)
+                const double ax = fabs(nx), ay = fabs(ny), az = fabs(nz);
+                const double lead = (ax >= ay && ax >= az) ? nx : (ay >= az ? ny : nz);
+                if (lead < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+            }
+        }
+        normals[3 * i] = nx; normals[3 * i + 1] = ny; normals[3 * i + 2] = nz;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // S1: parent radii + statistics.  mixture.cpp:70-95
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -158,6 +158,21 @@ class HemContext:
                                                 float(distance_delta), float(color_delta), float(decay_rate), pm))
         return self.num_levels
 
+    def registration_inputs(self, level: int, normals: bool = True) -> dict:
+        """What the reference hands to Open3D for a level (convert_gs_to_open3d_pc,
+        src/utils/point_cloud_converter.py:31-49), computed on the GPU: float64 points, sh2rgb
+        colours, [N,3,3] covariances and (optionally) covariance-derived normals."""
+        n = self.level_size(level)
+        out = dict(points=np.empty((n, 3), np.float64), colors=np.empty((n, 3), np.float64),
+                   covariances=np.empty((n, 3, 3), np.float64))
+        if normals:
+            out["normals"] = np.empty((n, 3), np.float64)
+        self._check(self._lib.hem_level_registration_inputs(
+            self._h, level, C.c_void_p(out["points"].ctypes.data), C.c_void_p(out["colors"].ctypes.data),
+            C.c_void_p(out["covariances"].ctypes.data),
+            C.c_void_p(out["normals"].ctypes.data) if normals else None))
+        return out
+
     def bind_output(self, level: int, xyz=None, colors=None, opacity=None, cov6=None, sh=None):
         """Bind caller-owned destination buffers (numpy views of pinned memory, or torch
         tensors) for `level`; the next ``build`` copies the level out on a second stream as

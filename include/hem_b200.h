@@ -108,6 +108,16 @@ int hem_level_copy(hem_ctx* ctx, int level,
                    float* xyz, float* color, float* opacity, float* cov6, float* sh,
                    float* weight, uint8_t* is_parent);
 
+/* "Next" row: the registration inputs the reference derives from a level on
+ * the host right after the HEM step — replaces the array part of convert_gs_to_open3d_pc
+ * (src/utils/point_cloud_converter.py:31-49): points [n*3] FP64, colors [n*3] FP64 = sh2rgb(DC)
+ * (src/utils/graphics_utils.py:72-73), cov33 [n*9] FP64 row-major (src/utils/general_utils.py:32-40),
+ * normals [n*3] FP64 = unit eigenvector of the smallest covariance eigenvalue (the reference's own
+ * TODO, point_cloud_converter.py:44-47; largest component positive).  Any pointer may be NULL;
+ * host or device pointers. */
+int hem_level_registration_inputs(hem_ctx* ctx, int level, double* points, double* colors, double* cov33,
+                                  double* normals);
+
 /* Optional copy/compute overlap for host callers: bind destination buffers (ideally pinned)
  * for level `level` (1..cluster_level) BEFORE hem_build_pyramid; the level is then copied out
  * on a second stream as soon as it is complete, while the next level is being built, and the

@@ -365,3 +365,25 @@ def test_gpu_awkward_geometry_vs_oracle(port, case):
         assert a["xyz"].shape == b["xyz"].shape and np.array_equal(a["is_parent"], b["is_parent"])
         assert group_relerr(a["xyz"], b["xyz"]) < 1e-6 and group_relerr(a["weight"], b["weight"]) < 1e-5
         assert group_relerr(a["sh"], b["sh"]) < 1e-5 and group_relerr(a["cov6"], b["cov6"]) < 5e-2
+
+
+def test_gpu_registration_inputs_match_reference_conversion(hemctx):
+    """§8f rank 2: points / sh2rgb colours / unpacked covariances exactly as the reference's
+    convert_gs_to_open3d_pc computes them in FP64, normals = smallest-eigenvalue eigenvector."""
+    c = synth(30000, seed=111, density=5000.0)
+    hemctx.build(*c.arrays(), cluster_level=2)
+    for l in (0, 2):
+        lv = hemctx.level(l)
+        ri = hemctx.registration_inputs(l)
+        assert np.array_equal(ri["points"], lv["xyz"].astype(np.float64))
+        assert np.array_equal(ri["colors"], lv["colors"].astype(np.float64) * 0.28209479177387814 + 0.5)
+        v = lv["cov6"].astype(np.float64)
+        full = np.stack([v[:, 0], v[:, 1], v[:, 2], v[:, 1], v[:, 3], v[:, 4], v[:, 2], v[:, 4], v[:, 5]], axis=1).reshape(-1, 3, 3)
+        assert np.array_equal(ri["covariances"], full)
+        w, V = np.linalg.eigh(full)
+        nref = V[:, :, 0]
+        dots = np.abs(np.einsum("ni,ni->n", nref, ri["normals"]))
+        gap = (w[:, 1] - w[:, 0]) / w[:, 2]
+        ok = gap > 1e-3                                      # eigenvector is ill-defined when the two smallest coincide
+        assert ok.mean() > 0.95 and dots[ok].min() > 1 - 1e-6
+        assert np.allclose(np.linalg.norm(ri["normals"], axis=1), 1.0, atol=1e-12)
