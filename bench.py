@@ -302,6 +302,20 @@ def run_b200_arm(a, rank, local_rank, world):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (level-0 launch of this
+    # very workload); bench.py itself never runs under a profiler
+    traffic, traffic_note = None, None
+    prof = os.path.join(ROOT, "profiles", "r01_v5_ncu_full_hot_kernels.csv")
+    if os.path.exists(prof) and a.n == 1_000_000:
+        import csv
+        rows = {r[0]: r for r in csv.reader(open(prof)) if r}
+        try:
+            traffic = (float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])) * 1e6
+            l0 = stats[0]
+            traffic_note = ("ncu --set full, level-0 k_gate launch (profiles/r01_v5_ncu_full_hot_kernels.csv); algorithmic bytes "
+                            f"of that launch = {(64 * l0['n_in'] + 60 * l0['n_parents'] + 12 * l0['n_pairs']) / 1e6:.1f} MB")
+        except (KeyError, ValueError, IndexError):
+            traffic = None
     gate_gbs = gate_bytes / (gate_ms * 1e-3) / 1e9 if gate_ms > 0 else 0.0
     mom_gbs = mom_bytes / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else 0.0
     lvl = [{"level": l, "n_in": stats[l]["n_in"], "n_parents": stats[l]["n_parents"], "n_pairs": stats[l]["n_pairs"],
@@ -315,7 +329,7 @@ def run_b200_arm(a, rank, local_rank, world):
                    "ms_per_step": e2e_ms / k_e2e, "steps": k_e2e},
            "gpu_launches": int(launches),
            "roofline": {"kernel": "hem::k_gate (gates + likelihood)", "bound": "hbm", "achieved": gate_gbs, "peak": peak,
-                        "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": gate_gbs / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                         "bytes_per_launch": gate_bytes / (a.steps * a.levels), "ms_per_launch": gate_ms / (a.steps * a.levels),
                         "note": "ALU/L2-bound by construction (SURVEY.md §8d): ~100 in-radius candidates per parent against 60 B of compulsory traffic per child"},
            "kernels": {"k_gate": {"gbs": gate_gbs, "frac": gate_gbs / peak, "ms_per_step": gate_ms / a.steps},
