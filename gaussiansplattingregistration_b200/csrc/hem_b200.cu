@@ -520,7 +520,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             if (fast || nchunks > 0) {
                 const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
                 k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
-                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
+                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>());
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
@@ -532,7 +532,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->csr_pad, (size_t)std::max<int64_t>(M, 1) * G * 8));
             if (nchunks > 0) {
                 k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
-                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, ctx->pool.as<uint2>(),
+                    ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>());
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
@@ -569,7 +569,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->ovf, (size_t)P * 16));
             k_claims<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
                                                                 ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
-                                                                ctx->ovf.as<uint4>(), (unsigned long long)P, d_counters);
+                                                                ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters);
             CK(cudaGetLastError()); ctx->n_launches++;
             k_sumlw_claims<<<blocks_for(n, 256), 256, 0, st>>>(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
                                                                 ctx->sumlw_mode == 2 ? ~0ull : 4096ull, n, d_sumlw);
@@ -593,6 +593,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = d_sumlw;
         M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
         M.counters = d_counters;
+        M.pool_cap = fast ? (unsigned long long)pool_cap : ~0ull;
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
@@ -639,7 +640,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     // the actual row count is read on the device, so one host sync closes the step
     k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
                                                          ctx->seed, rng_base, pp, distance_delta, ctx->valid.as<uint8_t>(),
-                                                         RAD_N.as<float>(), SAFE_N.as<uint8_t>(), PFLAG_N.as<uint32_t>(), d_ctl);
+                                                         RAD_N.as<float>(), SAFE_N.as<uint8_t>(), PFLAG_N.as<uint32_t>(),
+                                                         pool_cap_used ? (unsigned long long)pool_cap_used : ~0ull, d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
     k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
     CK(cudaGetLastError());

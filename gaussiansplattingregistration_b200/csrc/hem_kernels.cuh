@@ -367,6 +367,11 @@ constexpr int GATE_OUTCAP = 128;
 constexpr int GATE_TB = 4;                  // parents per work ticket
 // pool and chunk counters share one 64-bit word: pairs in the low 40 bits, chunks above
 constexpr int POOL_BITS = 40;
+// a step whose pair pool overflowed is redone by the host; until then nothing may follow the (unbounded) counts
+__device__ __forceinline__ bool pool_overflowed(const unsigned long long* counters, unsigned long long pool_cap)
+{
+    return (counters[C_POOL] & ((1ull << POOL_BITS) - 1ull)) > pool_cap;
+}
 
 // per-parent record in cell order, built once per step by k_ptab so that a gate warp starts
 // from ONE contiguous 80-byte read instead of a chain of dependent gathers
@@ -669,9 +674,10 @@ k_gate(GateArgs A)
 // pool -> cell-order CSR (what the moment kernel streams; a rank's slab of parents owns one
 // contiguous segment of it, which is what the ranks exchange)
 __global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned long long* __restrict__ counters,
-                             unsigned long long chunk_cap, const uint2* __restrict__ pool,
+                             unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
                              const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s)
 {
+    if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     // launched over the chunk capacity; the number of chunks written is read on the device
@@ -721,8 +727,9 @@ constexpr int CLAIM_K = 16;
 __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
                          const uint2* __restrict__ csr_s, int np, uint32_t* __restrict__ cnt_c,
                          uint2* __restrict__ claims, uint4* __restrict__ ovf, unsigned long long ovf_cap,
-                         unsigned long long* __restrict__ counters)
+                         unsigned long long pool_cap, unsigned long long* __restrict__ counters)
 {
+    if (pool_overflowed(counters, pool_cap)) return;
     const int lane = threadIdx.x & 31;
     const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= np) return;
@@ -751,9 +758,12 @@ __global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* 
     const uint2* row = claims + (size_t)c * CLAIM_K;
     if (m <= 4) {
         // common case: the claims sit in registers (two 16-byte loads), sorted by a 4-element network
-        const uint4 a = reinterpret_cast<const uint4*>(row)[0];
-        uint4 b = make_uint4(0u, 0u, 0u, 0u);
-        if (m > 2) b = reinterpret_cast<const uint4*>(row)[1];
+        // (slots beyond m were never written: read exactly the m entries)
+        uint4 a, b = make_uint4(0u, 0u, 0u, 0u);
+        if (m >= 2) a = reinterpret_cast<const uint4*>(row)[0];
+        else { const uint2 e = row[0]; a = make_uint4(e.x, e.y, 0u, 0u); }
+        if (m == 4) b = reinterpret_cast<const uint4*>(row)[1];
+        else if (m == 3) { const uint2 e = row[2]; b = make_uint4(e.x, e.y, 0u, 0u); }
         uint32_t k0 = a.x, k1 = m > 1 ? a.z : 0xffffffffu, k2 = m > 2 ? b.x : 0xffffffffu, k3 = m > 3 ? b.z : 0xffffffffu;
         uint32_t w0 = a.y, w1 = a.w, w2 = b.y, w3 = b.w;
 #define HEM_CSWAP(ka, wa, kb, wb) { if (kb < ka) { uint32_t t_ = ka; ka = kb; kb = t_; t_ = wa; wa = wb; wb = t_; } }
@@ -828,6 +838,7 @@ struct MomArgs {
     const float* sumlw;
     int t_begin, t_end;           // this rank's slab of parents (cell order)
     int by_rank;                  // 1: row index = canonical rank (final place); 0: row index = t (staging for the exchange)
+    unsigned long long pool_cap;  // the kernel does nothing if the pair pool overflowed (the host redoes the step)
     float4* ogeo; float* osh;
     unsigned long long* counters;
 };
@@ -844,6 +855,7 @@ k_moments(MomArgs A)
     //  0 mx 1 my 2 mz 3 weight | 4 c00 5 c01 6 c02 7 c11 | 8 c12 9 c22 10 opacity 11 det | 12 r 13 g 14 b 15 flag
     const int j = lane & 15;
     const bool is_cov = j >= 4 && j <= 9;
+    if (pool_overflowed(A.counters, A.pool_cap)) return;
     const int sa = (j <= 6) ? 0 : (j <= 8 ? 1 : 2);                 // first index of the outer-product term
     const int sb = (j == 4) ? 0 : ((j == 5 || j == 7) ? 1 : 2);     // second index
 
@@ -989,10 +1001,11 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
          const float* __restrict__ sumlw, int64_t n_in, uint64_t seed, uint64_t rng_base,
          float pp, float distance_delta, uint8_t* __restrict__ valid,
          float* __restrict__ radius_n, uint8_t* __restrict__ psafe_n, uint32_t* __restrict__ pflag_n,
-         Ctl* __restrict__ ctl)
+         unsigned long long pool_cap, Ctl* __restrict__ ctl)
 {
     __shared__ unsigned int s_red[8][10];
     __shared__ unsigned long long s_redd[8];
+    if (pool_overflowed(ctl->counters, pool_cap)) return;     // merged rows were not produced: the host redoes the step
     // pre-filter row count = parents + orphans, read on the device (the host learns it afterwards)
     const int64_t norph = (int64_t)orank[n_in - 1] + (sumlw[n_in - 1] == 0.0f ? 1 : 0);
     const int64_t n = np + norph;

@@ -387,3 +387,39 @@ def test_gpu_registration_inputs_match_reference_conversion(hemctx):
         ok = gap > 1e-3                                      # eigenvector is ill-defined when the two smallest coincide
         assert ok.mean() > 0.95 and dots[ok].min() > 1 - 1e-6
         assert np.allclose(np.linalg.norm(ri["normals"], axis=1), 1.0, atol=1e-12)
+
+
+def test_gpu_fast_flow_equals_general_flow():
+    """The single-sync fast flow (no white-box retention; what bench.py measures) and the general flow
+    (keep_pairs: per-stage syncs, canonical CSR) must produce bit-identical pyramids, also when the
+    pair pool overflows and the step is redone."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(300_000, seed=131, density=5000.0)
+    with HemContext(0, seed=7) as gen:
+        gen.set_option("keep_pairs", 1)
+        gen.build(*c.arrays(), cluster_level=4)
+        want = [gen.level(l, True) for l in range(5)]
+        want_stats = [gen.step_stats(s) for s in range(4)]
+    with HemContext(0, seed=7) as fast:
+        fast.build(*c.arrays(), cluster_level=4)
+        for l in range(5):
+            got = fast.level(l, True)
+            for k in KEYS:
+                assert np.array_equal(got[k], want[l][k]), f"fast flow differs at level {l} {k}"
+        for s in range(4):
+            st = fast.step_stats(s)
+            for k in ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out"):
+                assert st[k] == want_stats[s][k], (s, k, st[k], want_stats[s][k])
+    # dense cloud, tiny first guess for the pool: forces the overflow-and-redo path and the claim-table bail-out
+    d = synth(40_000, seed=132, density=100000.0)
+    with HemContext(0, seed=7) as gen:
+        gen.set_option("keep_pairs", 1)
+        gen.build(*d.arrays(), cluster_level=2)
+        want = [gen.level(l, True) for l in range(3)]
+        assert gen.step_stats(0)["n_pairs"] > 8 * 40_000
+    with HemContext(0, seed=7) as fast:
+        fast.build(*d.arrays(), cluster_level=2)
+        for l in range(3):
+            got = fast.level(l, True)
+            for k in KEYS:
+                assert np.array_equal(got[k], want[l][k]), f"dense fast flow differs at level {l} {k}"
