@@ -516,12 +516,20 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->csr_s, std::max<int64_t>(P, 1) * 8));
         CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
         CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
+        // claim-table regime decided here so that the single-GPU chunk copy can file the claims in the same pass
+        const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
+        const bool fuse_claims = use_claims && G == 1 && P > 0;
+        if (use_claims && P > 0) {
+            CKR(ensure(ctx, ctx->claims, (size_t)n * CLAIM_K * 8));
+            CKR(ensure(ctx, ctx->ovf, (size_t)P * 16));
+        }
         if (G == 1) {
             if (fast || nchunks > 0) {
                 const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
                 k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
-                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>());
+                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), ctx->ptab.as<uint2>(), d_cnt_c,
+                    fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
         } else {
@@ -533,7 +541,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             if (nchunks > 0) {
                 k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
-                    ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>());
+                    ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>(),
+                    nullptr, nullptr, nullptr, nullptr, 0ull);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             CKR(allgather_equal(ctx, ctx->csr_pad.p, 8, M));
@@ -547,7 +556,6 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         // ---- per-child normaliser ------------------------------------------------------------------
         // sparse regime (the benchmark's): claim table, 2 launches; dense regime: stable radix sort of the
         // canonical CSR by child.  Both add a child's claims in ascending parent rank (bit-identical).
-        const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
         const bool need_canon = !use_claims || ctx->keep_pairs;
         if (need_canon) {
             if (G > 1) {    // sharded: counts arrive in cell order, put them in canonical order here
@@ -565,12 +573,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             }
         }
         if (P > 0 && use_claims) {
-            CKR(ensure(ctx, ctx->claims, (size_t)n * CLAIM_K * 8));
-            CKR(ensure(ctx, ctx->ovf, (size_t)P * 16));
-            k_claims<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
-                                                                ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
-                                                                ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters);
-            CK(cudaGetLastError()); ctx->n_launches++;
+            if (!fuse_claims) {
+                k_claims<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                                                                    ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
+                                                                    ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters);
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
             k_sumlw_claims<<<blocks_for(n, 256), 256, 0, st>>>(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
                                                                 ctx->sumlw_mode == 2 ? ~0ull : 4096ull, n, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;

@@ -672,10 +672,15 @@ k_gate(GateArgs A)
 }
 
 // pool -> cell-order CSR (what the moment kernel streams; a rank's slab of parents owns one
-// contiguous segment of it, which is what the ranks exchange)
-__global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned long long* __restrict__ counters,
+// contiguous segment of it, which is what the ranks exchange).  On one GPU the same pass also files
+// every pair in its child's claim table (see k_claims below), saving a second sweep over the pairs.
+constexpr int CLAIM_K = 16;
+
+__global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long long* __restrict__ counters,
                              unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
-                             const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s)
+                             const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s,
+                             const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c, uint2* __restrict__ claims,
+                             uint4* __restrict__ ovf, unsigned long long ovf_cap)
 {
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
     const int lane = threadIdx.x & 31;
@@ -685,7 +690,20 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, const unsigned lo
     if (c >= nchunks) return;
     const uint4 ch = chunks[c];
     const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
-    for (uint32_t k = lane; k < ch.z; k += 32) csr_s[dst + k] = pool[(size_t)ch.y + k];
+    const uint32_t srank = claims ? ptab[ch.x].y : 0u;
+    for (uint32_t k = lane; k < ch.z; k += 32) {
+        const uint2 p = pool[(size_t)ch.y + k];
+        csr_s[dst + k] = p;
+        if (claims) {
+            const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
+            if (slot < (uint32_t)CLAIM_K) {
+                claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
+            } else {
+                const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+                if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
+            }
+        }
+    }
 }
 
 // per-parent pair counts from cell order to ascending canonical parent order
@@ -722,7 +740,6 @@ __global__ void k_csr_canon(const uint2* __restrict__ ptab, const uint32_t* __re
 // bit-identical to the sort path and run-to-run deterministic.  Claims beyond CLAIM_K go to a
 // global overflow list that the child scans (never reached at the benchmark densities).
 // ---------------------------------------------------------------------------
-constexpr int CLAIM_K = 16;
 
 __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
                          const uint2* __restrict__ csr_s, int np, uint32_t* __restrict__ cnt_c,
