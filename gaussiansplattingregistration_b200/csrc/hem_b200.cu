@@ -71,7 +71,7 @@ struct hem_ctx {
     bool dense_hint = false;       // last step had more than 4 accepted pairs per component
     size_t pool_min = 0;           // pair pool size learned from an overflow
     int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
-    double cell_scale = 0.5;
+    double cell_scale = 0.55;
     bool rng_base_set = false;
     uint64_t rng_base = 0;
     int F = 0, Fp = 0;
@@ -368,7 +368,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 if (!std::isfinite(bmin[a])) bmin[a] = -FLT_MAX;
                 if (!std::isfinite(bmax[a])) bmax[a] = FLT_MAX;
             }
-            double h = ps.n_radius ? ctx->cell_scale * ((double)ps.sum_radius_fx / 65536.0 / (double)ps.n_radius) : 1.0;
+            // cell edge = cell_scale x geometric mean of the parent radii
+            double h = ps.n_radius ? ctx->cell_scale * std::exp2((double)ps.sum_radius_fx / 65536.0 / (double)ps.n_radius - 128.0) : 1.0;
             if (!(h > 0)) h = 1.0;
             const double max_cells = 1 << 24;
             double ext[3];

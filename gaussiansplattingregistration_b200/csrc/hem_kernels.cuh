@@ -52,8 +52,10 @@ struct Ctl {
     unsigned int n_radius;          // parents with finite positive radius
     unsigned int n_parents;
     unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
-    unsigned long long sum_radius_fx;   // sum of min(radius, 65536) in 2^-16 units: integer adds are order-independent,
-                                        // so the grid cell size (and with it every summation order) is deterministic
+    unsigned long long sum_radius_fx;   // sum of (log2(radius) + 128) in 2^-16 units over the parents with a finite positive
+                                        // radius: the grid cell is sized from the GEOMETRIC mean radius (robust against the
+                                        // heavy tail of splat scales); integer adds are order-independent, so the cell size —
+                                        // and with it every summation order — is deterministic
     // the same statistics for the NEXT level, produced by k_finish while it finalises the output rows
     // (so the next step starts without a prep kernel and without a host sync)
     unsigned int nx_bbmax_u[3];
@@ -78,7 +80,7 @@ __global__ void k_zero(uint4* __restrict__ p, size_t n16)
         p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-__device__ __forceinline__ unsigned long long radius_fx(float r) { return (unsigned long long)(fminf(r, 65536.0f) * 65536.0f); }
+__device__ __forceinline__ unsigned long long radius_fx(float r) { return (unsigned long long)((log2f(r) + 128.0f) * 65536.0f); }
 
 __device__ __forceinline__ int f2ord(float f)
 {

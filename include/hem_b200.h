@@ -58,7 +58,7 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
 /* Options (all optional):
  *   "timing"      1 -> record CUDA events around every stage (hem_step_stats ms fields)
  *   "keep_pairs"  1 -> retain each step's (parent, child, wL) lists for hem_step_pairs
- *   "cell_scale"  grid cell = cell_scale * mean parent radius (default 0.5)
+ *   "cell_scale"  grid cell = cell_scale * geometric-mean parent radius (default 0.55)
  *   "smd_prefilter" 1 (default) -> certified Mahalanobis pre-test inside the KLD gate (same
  *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
  *   "sumlw_mode"  0 (default) auto, 1 stable radix sort by child, 2 claim table: two bit-identical
