@@ -70,6 +70,10 @@ struct hem_ctx {
     Ctl prep_stats;
     bool dense_hint = false;       // last step had more than 4 accepted pairs per component
     size_t pool_min = 0;           // pair pool size learned from an overflow
+    // robust grid box of the current build (percentile range of the level-0 means, see k_boxhist)
+    bool box_valid = false;
+    float box_lo[3] = { 0, 0, 0 }, box_hi[3] = { 0, 0, 0 };
+    double box_q = 5e-4;
     int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
     double cell_scale = 0.55;
     bool rng_base_set = false;
@@ -88,7 +92,7 @@ struct hem_ctx {
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
     DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf;
+    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
@@ -266,6 +270,53 @@ int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk)
     return HEM_OK;
 }
 
+// percentile box of the means of a level (at most two histogram passes), see k_boxhist
+int robust_box(hem_ctx* ctx, const float4* geo, int64_t n, const float bmin[3], const float bmax[3])
+{
+    cudaStream_t st = ctx->stream;
+    CKR(ensure(ctx, ctx->boxhist, 3 * BOX_BINS * 4));
+    std::vector<unsigned int> hh(3 * BOX_BINS);
+    float lo[3] = { bmin[0], bmin[1], bmin[2] }, hi[3] = { bmax[0], bmax[1], bmax[2] };
+    for (int pass = 0; pass < 2; ++pass) {
+        float sc[3];
+        bool any = false;
+        for (int a = 0; a < 3; ++a) {
+            const double w = (double)hi[a] - (double)lo[a];
+            sc[a] = (w > 0 && std::isfinite(w)) ? (float)(BOX_BINS / w) : 0.0f;
+            any |= sc[a] > 0;
+        }
+        if (!any) break;
+        CK(cudaMemsetAsync(ctx->boxhist.p, 0, 3 * BOX_BINS * 4, st));
+        k_boxhist<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
+            geo, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2], ctx->boxhist.as<unsigned int>());
+        CK(cudaGetLastError()); ctx->n_launches++;
+        CK(cudaMemcpyAsync(hh.data(), ctx->boxhist.p, 3 * BOX_BINS * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        bool shrunk = false;
+        for (int a = 0; a < 3; ++a) {
+            if (!(sc[a] > 0)) continue;
+            uint64_t tot = 0;
+            for (int b = 0; b < BOX_BINS; ++b) tot += hh[a * BOX_BINS + b];
+            const uint64_t cut = (uint64_t)(ctx->box_q * (double)tot);
+            int b0 = 0, b1 = BOX_BINS - 1;
+            uint64_t acc = 0;
+            while (b0 < BOX_BINS - 1 && acc + hh[a * BOX_BINS + b0] <= cut) acc += hh[a * BOX_BINS + b0++];
+            acc = 0;
+            while (b1 > b0 && acc + hh[a * BOX_BINS + b1] <= cut) acc += hh[a * BOX_BINS + b1--];
+            const double bw = ((double)hi[a] - (double)lo[a]) / BOX_BINS;
+            const double nlo = (double)lo[a] + (b0 - 1) * bw, nhi = (double)lo[a] + (b1 + 2) * bw;   // one bin of margin
+            const double oldw = (double)hi[a] - (double)lo[a];
+            const float flo = (float)std::max(nlo, (double)lo[a]), fhi = (float)std::min(nhi, (double)hi[a]);
+            if ((double)fhi - (double)flo < 0.125 * oldw) shrunk = true;
+            lo[a] = flo; hi[a] = fhi;
+        }
+        if (!shrunk) break;       // the bulk fills the histogram range: resolution is fine
+    }
+    for (int a = 0; a < 3; ++a) { ctx->box_lo[a] = lo[a]; ctx->box_hi[a] = hi[a]; }
+    ctx->box_valid = true;
+    return HEM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // one clustering step: levels[l] -> levels[l+1]
 // ---------------------------------------------------------------------------
@@ -367,6 +418,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 bmax[a] = ps.bbmax_u[a] ? u2f(ps.bbmax_u[a]) : 0.0f;
                 if (!std::isfinite(bmin[a])) bmin[a] = -FLT_MAX;
                 if (!std::isfinite(bmax[a])) bmax[a] = FLT_MAX;
+            }
+            // the grid spans the robust (percentile) box of the build's level 0; later levels lie inside it
+            if (!ctx->box_valid) CKR(robust_box(ctx, geo, n, bmin, bmax));
+            for (int a = 0; a < 3; ++a) {
+                bmin[a] = std::max(bmin[a], ctx->box_lo[a]);
+                bmax[a] = std::max(bmin[a], std::min(bmax[a], ctx->box_hi[a]));
             }
             // cell edge = cell_scale x geometric mean of the parent radii
             double h = ps.n_radius ? ctx->cell_scale * std::exp2((double)ps.sum_radius_fx / 65536.0 / (double)ps.n_radius - 128.0) : 1.0;
@@ -869,7 +926,7 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf };
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist };
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -897,6 +954,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
+    else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
     else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }
@@ -925,6 +983,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     ctx->pairs.assign(ctx->keep_pairs ? cluster_level : 0, StepPairs());
 
     ctx->prep_valid = false;
+    ctx->box_valid = false;
     // level 0 = the input (Mixture::initMixture, mixture.cpp:287-333)
     Level& L0 = ctx->levels[0];
     L0.n = n;

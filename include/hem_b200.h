@@ -65,6 +65,8 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 ways of adding a child's claims in ascending parent order
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
  *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
+ *   "box_quantile" the grid spans the [q, 1-q] percentile range of the level-0 means per axis (default 5e-4;
+ *                 0 = full bounding box); outliers are clamped into border cells, results do not depend on it
  *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
  *                 (the reference consumes one draw per level-0 component first,
  *                 src/cpp_ext/src/mixture.cpp:330, then one per pre-filter
