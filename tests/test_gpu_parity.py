@@ -482,3 +482,26 @@ def test_gpu_far_outliers_robust_grid_box(port):
                               what=f"percentile box vs full box, step {s}")
     for l in range(3):
         assert_level_close(la[l], lb[l], tol=1e-5, what=f"percentile box vs full box, level {l}")
+
+
+def test_gpu_plane_inlier_merging_matches_oracle(port):
+    """§8f rank 3: the plane-merging caller = unselected splats + one HEM pyramid per plane's inliers,
+    concatenated per level in the reference's order (qt_plane_merging.py:132-177)."""
+    from gaussiansplattingregistration_b200.hem import HemParams
+    from gaussiansplattingregistration_b200.plane_merging import merge_plane_inliers
+    c = synth(20000, seed=151, density=5000.0, sh_degree=1)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(c.n)
+    planes = [np.sort(perm[:6000]), np.sort(perm[6000:9000]), np.zeros(0, np.int64)]
+    p = HemParams(cluster_level=2)
+    got = merge_plane_inliers(*c.arrays(), planes, p, seed=21)
+    unsel = np.setdiff1d(np.arange(c.n), np.concatenate(planes))
+    runs = [port.run(*(a[ix] for a in c.arrays()), levels=2, seed=21) for ix in planes[:2]]
+    for d in range(2):
+        want = {k: np.concatenate([a[unsel]] + [r.level(d + 1)[k] for r in runs]) for k, a in
+                zip(("xyz", "colors", "opacity", "cov6", "sh"), c.arrays())}
+        assert np.array_equal(got[d]["xyz"][:len(unsel)], c.xyz[unsel])          # unselected copied verbatim, first
+        if d == 0:
+            assert_level_close(got[d], want, what=f"plane merging level {d}")
+        else:
+            assert abs(got[d]["xyz"].shape[0] - want["xyz"].shape[0]) <= 4
