@@ -11,6 +11,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -43,6 +44,7 @@ struct Level {
 struct StepStats {
     int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0, n_certified = 0;
     double cell_size = 0, max_radius = 0;
+    double ms_host = 0;       // host time spent enqueueing the step (up to its closing sync)
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
 };
 
@@ -332,6 +334,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     const float pp = 1.0f / hem_reduction;
     S = StepStats();
     S.n_in = n;
+    const auto host_t0 = std::chrono::steady_clock::now();
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_BEGIN], st));
 
     if (n == 0) { out.n = 0; return HEM_OK; }
@@ -711,6 +714,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CK(cudaGetLastError()); ctx->n_launches++;
     k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
     CK(cudaGetLastError());
+    const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     CK(cudaStreamSynchronize(st));                                      // sync C
     memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
     if (have_pairs) {
@@ -759,6 +763,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         out.n = nout;
     }
     S.n_out = out.n;
+    S.ms_host = host_ms;
     // hand the next level its prep (invalid as soon as the filter erased rows: positions shifted)
     ctx->prep_valid = (ninvalid == 0);
     ctx->prep_level = l + 1;
@@ -1150,6 +1155,7 @@ int hem_step_stats(const hem_ctx* ctx, int step, double* out)
     out[8] = S.max_radius;
     for (int i = 0; i < 9; ++i) out[9 + i] = S.ms[i];
     out[18] = (double)S.n_certified;
+    out[19] = S.ms_host;
     return HEM_OK;
 }
 

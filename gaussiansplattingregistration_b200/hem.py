@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi
 
 STAT_NAMES = ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out", "grid_cells", "cell_size",
-              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments", "n_certified_parents")
+              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments", "n_certified_parents", "ms_host_enqueue")
 
 
 @dataclass

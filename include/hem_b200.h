@@ -137,9 +137,10 @@ int hem_clear_outputs(hem_ctx* ctx);
  *   9 ms_total  10 ms_prep  11 ms_grid  12 ms_gate  13 ms_sumlw  14 ms_moments  15 ms_compact
  *   16 ms_k_gate (the gate kernel alone)  17 ms_k_moments (the moment kernel alone)
  *   18 n_certified_parents (parents whose covariance is certified for the smd pre-test)
+ *   19 ms_host_enqueue (host wall time spent enqueueing the step, up to its closing sync)
  * ms_* are CUDA-event times on the context's stream and are 0 unless the
  * "timing" option is set. */
-#define HEM_STEP_STATS_LEN 19
+#define HEM_STEP_STATS_LEN 20
 int hem_step_stats(const hem_ctx* ctx, int step, double* out);
 
 /* Cumulative counters of the context: "launches" (kernels of this library
