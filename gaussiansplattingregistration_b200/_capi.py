@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HEM_B200_LIB") or os.path.join(_HERE, "libhem_b200.so")   # override: kernel experiments only
 
 STEP_STATS_LEN = 20
+ICP_RESULT_LEN = 24
 NCCL_ID_BYTES = 128
 
 _f = C.POINTER(C.c_float)
@@ -37,6 +38,10 @@ SIGNATURES = {
     "hem_level_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "hem_level_registration_inputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hem_icp_point_to_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
+                                         C.c_double, C.c_double, C.c_int, _d, C.c_void_p]),
+    "hem_icp_multiscale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _d, C.POINTER(C.c_int32), C.c_double, C.c_double,
+                                     C.c_void_p, _d]),
     "hem_bind_output": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "hem_clear_outputs": (C.c_int, [C.c_void_p]),
     "hem_step_stats": (C.c_int, [C.c_void_p, C.c_int, _d]),

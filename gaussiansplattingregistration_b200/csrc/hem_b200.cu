@@ -6,6 +6,7 @@
 // the CUDA path or returns an error.
 #include "../../include/hem_b200.h"
 #include "hem_kernels.cuh"
+#include "hem_icp.cuh"
 
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -110,6 +111,12 @@ struct hem_ctx {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+
+    // ICP consumer (hem_icp.cuh)
+    DevBuf icp_src, icp_tgt, icp_box, icp_key, icp_key2, icp_val, icp_val2, icp_rows, icp_start, icp_part, icp_state, icp_corr;
+    hem::icp::State* h_icp = nullptr;           // pinned + mapped
+    hem::icp::State* h_icp_dev = nullptr;
+    cudaEvent_t ev_icp0 = nullptr, ev_icp1 = nullptr;
 };
 
 namespace {
@@ -931,10 +938,14 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist };
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist,
+                      &ctx->icp_src, &ctx->icp_tgt, &ctx->icp_box, &ctx->icp_key, &ctx->icp_key2, &ctx->icp_val, &ctx->icp_val2,
+                      &ctx->icp_rows, &ctx->icp_start, &ctx->icp_part, &ctx->icp_state, &ctx->icp_corr };
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->h_icp) cudaFreeHost(ctx->h_icp);
+    for (cudaEvent_t e : { ctx->ev_icp0, ctx->ev_icp1 }) if (e) cudaEventDestroy(e);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (cudaEvent_t e : { ctx->ev_geo, ctx->ev_sh, ctx->ev_level }) if (e) cudaEventDestroy(e);
@@ -1224,3 +1235,5 @@ int hem_slab_range(int64_t n_parents, int rank, int world, int64_t* begin, int64
 }
 
 } // extern "C"
+
+#include "hem_icp_host.inl"

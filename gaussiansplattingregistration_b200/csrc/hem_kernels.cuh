@@ -2,15 +2,20 @@
 //
 // One step = reference Mixture::createClusterLevel (src/cpp_ext/src/mixture.cpp:66-285).
 // Stage map (DESIGN.md has the data-flow picture and the byte accounting):
-//   S1  k_prep            parent radius, bbox / radius statistics            mixture.cpp:70-95
-//   S2  k_cellkey + radix sort + k_sorted_gather   uniform grid              pointindex.cpp:55-108
-//   S3  k_gate            radius / colour / KLD / parent-exclusion gates,    mixture.cpp:106-164
+//   S1  k_prep (level 0) / k_finish of the previous step (levels >= 1)
+//                         parent radius, certificates, bbox / radius statistics     mixture.cpp:70-95
+//       k_boxhist         percentile box of the level-0 means (grid extent only)
+//   S2  k_cellkey + radix sort + k_sorted_gather + k_ptab   uniform grid            pointindex.cpp:55-108
+//   S3  k_gate            radius / colour / KLD / parent-exclusion gates,           mixture.cpp:106-164
 //                         likelihood wL, pooled pair emission
-//       k_chunk_copy      pool -> parent-major CSR (ascending parent index)
-//       radix sort + k_segsum   per-child normaliser sumLw, ascending parent order  mixture.cpp:143-163
-//   S4  k_moments         fused weight/mean/cov/colour/opacity/SH moments    mixture.cpp:168-247
-//   S5  k_orphans         orphan copy, flags, validity                       mixture.cpp:251-282
-//       k_compact_rows    validity filter compaction (only if something was dropped)
+//       k_chunk_copy      pool -> cell-order CSR (+ claim-table insertion on one GPU)
+//       k_claims / k_sumlw_claims   per-child normaliser sumLw, ascending parent order  mixture.cpp:143-163
+//       (k_cnt_canon / k_csr_canon / radix sort / k_segsum: the sort-based path of the same sum)
+//   S4  k_moments         fused weight/mean/cov/colour/opacity/SH moments           mixture.cpp:168-247
+//   S5  k_orphans         orphan copy                                               mixture.cpp:251-282
+//       k_finish          det, Philox flag, validity, next step's S1
+//       k_valid_flag / k_compact_rows   validity filter compaction (only if something was dropped)
+//   I/O k_import / k_export / k_registration_inputs, k_zero / k_publish (control block)
 #pragma once
 #include "hem_math.cuh"
 #include <cfloat>

@@ -28,6 +28,35 @@ class HemParams:
     cluster_level: int = 3
 
 
+@dataclass
+class IcpResult:
+    """Field names of Open3D's RegistrationResult (what the reference reads:
+    qt_multiscale_registrator.py:151-161) plus diagnostics."""
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    iterations: int
+    n_correspondences: int
+    stop_reason: int          # 1 converged, 2 max_iteration, 3 fewer than 3 correspondences
+    ms_device: float
+    grid_cells: int
+    cell_size: float
+    correspondence: np.ndarray | None = None     # [n_source] target index or -1
+
+    @property
+    def correspondence_set(self) -> np.ndarray:
+        """[K,2] (source index, target index) pairs like Open3D's correspondence_set."""
+        if self.correspondence is None:
+            raise ValueError("run with with_correspondences=True")
+        src = np.nonzero(self.correspondence >= 0)[0]
+        return np.stack([src, self.correspondence[src]], 1).astype(np.int32)
+
+    @staticmethod
+    def from_flat(r, corr) -> "IcpResult":
+        return IcpResult(np.array(r[:16]).reshape(4, 4), float(r[16]), float(r[17]), int(r[18]), int(r[19]), int(r[20]),
+                         float(r[21]), int(r[22]), float(r[23]), corr)
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -172,6 +201,46 @@ class HemContext:
             C.c_void_p(out["covariances"].ctypes.data),
             C.c_void_p(out["normals"].ctypes.data) if normals else None))
         return out
+
+    def icp(self, source, target, init=None, max_correspondence: float = 5.0, relative_fitness: float = 1e-6,
+            relative_rmse: float = 1e-6, max_iteration: int = 30, with_correspondences: bool = False) -> "IcpResult":
+        """Point-to-point ICP on the GPU with Open3D's definitions (``hem_icp_point_to_point``; replaces
+        the registration_icp call of the reference's do_icp_registration,
+        src/utils/local_registration_util.py:76-100).  source/target: [n,3] float64 numpy arrays or
+        torch CUDA tensors."""
+        ps, ks = _ptr(source if _is_torch(source) else np.asarray(source, np.float64))
+        pt, kt = _ptr(target if _is_torch(target) else np.asarray(target, np.float64))
+        for a in (ks, kt):
+            if _is_torch(a):
+                assert str(a.dtype) == "torch.float64", "ICP points must be float64"
+        ns, nt = int(ks.shape[0]), int(kt.shape[0])
+        res = np.zeros(_capi.ICP_RESULT_LEN, np.float64)
+        T0 = None if init is None else np.ascontiguousarray(np.asarray(init, np.float64).reshape(4, 4))
+        corr = np.empty(ns, np.int32) if with_correspondences else None
+        self._check(self._lib.hem_icp_point_to_point(
+            self._h, ps, ns, pt, nt, None if T0 is None else C.c_void_p(T0.ctypes.data), float(max_correspondence),
+            float(relative_fitness), float(relative_rmse), int(max_iteration),
+            res.ctypes.data_as(C.POINTER(C.c_double)), None if corr is None else C.c_void_p(corr.ctypes.data)))
+        return IcpResult.from_flat(res, corr)
+
+    def icp_multiscale(self, target_ctx: "HemContext", max_correspondences, max_iterations, init=None,
+                       relative_fitness: float = 1e-6, relative_rmse: float = 1e-6) -> list:
+        """Coarse-to-fine ICP of this context's pyramid (source) onto ``target_ctx``'s pyramid
+        (``hem_icp_multiscale``; the loop of MultiScaleRegistratorMixture._register_main_point_clouds,
+        src/gui/workers/registration/qt_multiscale_registrator.py:203-230): scale i uses level
+        ``num_levels-1-i`` of both pyramids.  Returns one IcpResult per scale; the last one is the answer."""
+        k = len(max_correspondences)
+        if k != len(max_iterations):
+            raise ValueError("The number of iteration and voxel values provided do not match.")
+        mc = np.ascontiguousarray(max_correspondences, np.float64)
+        mi = np.ascontiguousarray(max_iterations, np.int32)
+        T0 = None if init is None else np.ascontiguousarray(np.asarray(init, np.float64).reshape(4, 4))
+        res = np.zeros((k, _capi.ICP_RESULT_LEN), np.float64)
+        self._check(self._lib.hem_icp_multiscale(
+            self._h, target_ctx._h, k, mc.ctypes.data_as(C.POINTER(C.c_double)), mi.ctypes.data_as(C.POINTER(C.c_int32)),
+            float(relative_fitness), float(relative_rmse), None if T0 is None else C.c_void_p(T0.ctypes.data),
+            res.ctypes.data_as(C.POINTER(C.c_double))))
+        return [IcpResult.from_flat(r, None) for r in res]
 
     def bind_output(self, level: int, xyz=None, colors=None, opacity=None, cov6=None, sh=None):
         """Bind caller-owned destination buffers (numpy views of pinned memory, or torch

@@ -120,6 +120,41 @@ int hem_level_copy(hem_ctx* ctx, int level,
 int hem_level_registration_inputs(hem_ctx* ctx, int level, double* points, double* colors, double* cov33,
                                   double* normals);
 
+/* "Next" row: the consumer of the pyramid.  Point-to-point ICP with the definitions of
+ * the Open3D call the reference makes per level — replaces
+ *   o3d.pipelines.registration.registration_icp(source, target, max_correspondence, init,
+ *       TransformationEstimationPointToPoint(), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration))
+ * as issued by do_icp_registration (src/utils/local_registration_util.py:76-100) with the default
+ * LocalRegistrationParams (src/params/registration_parameters.py:8-15: point-to-point, no robust loss).
+ * Open3D is a third-party dependency (pinned 0.16.0, requirements.txt:3) and is not part of the reference tree;
+ * the algorithm restated is RegistrationICP of its Registration.cpp: correspondences = nearest target point of each
+ * transformed source point with distance < max_correspondence; fitness = #correspondences / n_source;
+ * inlier_rmse = sqrt(sum d^2 / #correspondences); update = rigid least squares (umeyama, no scale); stop when both
+ * |d fitness| < relative_fitness and |d inlier_rmse| < relative_rmse, or after max_iteration updates.
+ *   source [n_source*3], target [n_target*3]: FP64 points, host or device (hem_level_registration_inputs layout)
+ *   init: 4x4 row-major FP64, NULL = identity (host pointer)
+ *   result (host): 0..15 transformation (row-major 4x4)  16 fitness  17 inlier_rmse  18 iterations (updates applied)
+ *                  19 n_correspondences  20 stop reason (1 converged, 2 max_iteration, 3 fewer than 3 correspondences)
+ *                  21 ms on the device  22 grid cells  23 grid cell size
+ *   correspondence [n_source] or NULL: index of the matched target point under the final transformation, -1 = none
+ *                  (Open3D's correspondence_set_); host or device. */
+#define HEM_ICP_RESULT_LEN 24
+int hem_icp_point_to_point(hem_ctx* ctx, const double* source, int64_t n_source, const double* target, int64_t n_target,
+                           const double* init, double max_correspondence, double relative_fitness, double relative_rmse,
+                           int max_iteration, double* result, int32_t* correspondence);
+
+/* Coarse-to-fine driver over two pyramids held in two contexts on the same device — replaces
+ * MultiScaleRegistratorMixture._register_main_point_clouds (src/gui/workers/registration/qt_multiscale_registrator.py:203-230):
+ * scale i registers level (num_levels-1-i) of the source pyramid to the same level of the target pyramid
+ * (pc_list[-(i+1)]: coarsest first, level 0 = the full cloud last) with max_correspondence[i] (voxel_values) and
+ * max_iteration[i] (iter_values), starting from the previous scale's transformation.  n_scales must equal
+ * hem_num_levels of both contexts (the reference's own validity checks, :170-194, same messages).  The level means
+ * go from the canonical rows to the FP64 search structures on the device; nothing crosses PCIe but the results:
+ * results [n_scales * HEM_ICP_RESULT_LEN], one block per scale in the layout above. */
+int hem_icp_multiscale(hem_ctx* source_ctx, hem_ctx* target_ctx, int n_scales, const double* max_correspondence,
+                       const int32_t* max_iteration, double relative_fitness, double relative_rmse, const double* init,
+                       double* results);
+
 /* Optional copy/compute overlap for host callers: bind destination buffers (ideally pinned)
  * for level `level` (1..cluster_level) BEFORE hem_build_pyramid; the level is then copied out
  * on a second stream as soon as it is complete, while the next level is being built, and the

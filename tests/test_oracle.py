@@ -128,3 +128,35 @@ def test_oracle_edge_cases(port):
     assert np.array_equal(ch["child"], np.arange(500, dtype=np.uint32))
     assert_level_close({k: v for k, v in r.level(1).items() if k != "is_parent"},
                        {k: v for k, v in r.level(0).items() if k != "is_parent"}, tol=1e-5)
+
+
+def test_icp_oracle_recovers_a_known_rigid_motion_and_validates_arguments():
+    """The ICP oracle (restated Open3D RegistrationICP, parity unpinned by the reference) on a noiseless copy, and the
+    host-side validity checks of the registration mirror (no GPU involved)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import icp_oracle
+    from gaussiansplattingregistration_b200 import registration as reg
+    rng = np.random.default_rng(3)
+    tgt = rng.uniform(0, 1, (4000, 3))
+    th = 0.04
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    t = np.array([0.01, -0.015, 0.02])
+    src = (tgt - t) @ R                     # R src + t = tgt
+    r = icp_oracle.registration_icp(src, tgt, 0.1, None, 1e-6, 1e-6, 50)
+    assert r["fitness"] == 1.0 and r["inlier_rmse"] < 1e-12 and r["stop_reason"] == 1
+    assert np.abs(r["transformation"][:3, :3] - R).max() < 1e-12 and np.abs(r["transformation"][:3, 3] - t).max() < 1e-12
+    assert np.array_equal(r["correspondence"], np.arange(4000))
+    # a reflection-prone (planar) configuration still yields a proper rotation
+    U = icp_oracle.umeyama_rigid(src * [1, 1, 0], tgt * [1, 1, 0])
+    assert abs(np.linalg.det(U[:3, :3]) - 1.0) < 1e-12
+    with pytest.raises(ValueError, match="do not match"):
+        reg.multiscale_registration([src, src], [tgt, tgt], None, [0.1, 0.05], [10])
+    with pytest.raises(ValueError, match="differ in size"):
+        reg.multiscale_registration([src, src], [tgt], None, [0.1, 0.05], [10, 5])
+    with pytest.raises(ValueError, match="no downscaled mixtures"):
+        reg.multiscale_registration([src], [tgt], None, [0.1], [10])
+    with pytest.raises(ValueError, match="mixture levels do not match"):
+        reg.multiscale_registration([src, src, src], [tgt, tgt, tgt], None, [0.1, 0.05], [10, 5])
+    assert reg.LocalRegistrationParams().registration_type is reg.LocalRegistrationType.ICP_Point_To_Point
