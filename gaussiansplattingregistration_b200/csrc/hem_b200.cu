@@ -79,6 +79,7 @@ struct hem_ctx {
     double box_q = 5e-4;
     int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
     double cell_scale = 0.55;
+    double cell_occupancy = 1.3;   // lower bound of the cell edge in units of the mean component spacing
     bool rng_base_set = false;
     uint64_t rng_base = 0;
     int F = 0, Fp = 0;
@@ -175,6 +176,38 @@ int to_device(hem_ctx* ctx, const void* src, size_t bytes, DevBuf& stage, const 
     ctx->bytes_h2d += bytes;
     *out = stage.p;
     return HEM_OK;
+}
+
+int g_gate_tb = 0;    // HEM_GATE_TICKET in the environment forces the gate ticket size (A/B measurements)
+bool g_pdl = true;   // HEM_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)
+
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the stream is
+// still draining; every kernel launched this way calls pdl_enter() (griddepcontrol.wait) before it touches
+// memory, so the data dependence is unchanged and only the launch latency between dependent kernels goes.
+template <class... KArgs> struct PdlLaunch {
+    void (*kernel)(KArgs...);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    template <class... Args> void operator()(Args&&... args)
+    {
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError()
+    }
+};
+template <class... KArgs> PdlLaunch<KArgs...> pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    PdlLaunch<KArgs...> L;
+    L.kernel = kernel;
+    memset(&L.cfg, 0, sizeof L.cfg);
+    L.cfg.gridDim = grid;
+    L.cfg.blockDim = block;
+    L.cfg.dynamicSmemBytes = smem;
+    L.cfg.stream = st;
+    memset(&L.attr, 0, sizeof L.attr);
+    L.attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    L.attr.val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    return L;
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
@@ -378,17 +411,17 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, PFLAG, n * 4));
     }
     CKR(ensure(ctx, ctx->prank, n * 4));
-    k_zero<<<(unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
+    pdl(k_zero, (unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st)(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
     CK(cudaGetLastError()); ctx->n_launches++;
     Ctl ps;
     if (carried) {
         // radii, flags, certificates and statistics of this level were produced by the previous step's k_finish
         ps = ctx->prep_stats;
     } else {
-        k_prep<<<(unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st>>>(
+        pdl(k_prep, (unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st)(
             geo, n, distance_delta, RAD.as<float>(), PFLAG.as<uint32_t>(), SAFE.as<uint8_t>(), d_ctl);
         CK(cudaGetLastError()); ctx->n_launches++;
-        k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+        pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));                                  // sync A (level 0 / after an erasing filter only)
         ps = *ctx->h_ctl;
@@ -441,6 +474,13 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             const double max_cells = 1 << 24;
             double ext[3];
             for (int a = 0; a < 3; ++a) ext[a] = std::max(0.0, (double)bmax[a] - (double)bmin[a]);
+            // ... but never much finer than the component spacing: on the coarse levels the merged Gaussians are
+            // few and wide, and a radius-derived cell would leave most cells empty (the gate then spends its time
+            // on cell-range lookups instead of candidates)
+            if (ctx->cell_occupancy > 0 && n > 0) {
+                const double vol = ext[0] * ext[1] * ext[2];
+                if (vol > 0 && std::isfinite(vol)) h = std::max(h, ctx->cell_occupancy * std::cbrt(vol / (double)n));
+            }
             for (int it = 0; it < 64; ++it) {
                 double cells = 1;
                 bool too_long = false;
@@ -470,14 +510,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->cell_start, ((size_t)ncell + 1) * 4));
         CKR(ensure(ctx, ctx->psorted, np * 4));
         CKR(ensure(ctx, ctx->nsel, 8));
-        k_cellkey<<<blocks_for(n, 256), 256, 0, st>>>(geo, n, g, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
+        pdl(k_cellkey, blocks_for(n, 256), 256, 0, st)(geo, n, g, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
         CK(cudaGetLastError()); ctx->n_launches++;
         const int kbits = bits_for(ncell - 1);
         CKR(cub_call(ctx, [&](void* t, size_t& b) {
             return cub::DeviceRadixSort::SortPairs(t, b, ctx->key.as<uint32_t>(), ctx->key2.as<uint32_t>(),
                                                    ctx->val.as<uint32_t>(), ctx->val2.as<uint32_t>(), (int)n, 0, kbits, st);
         }));
-        k_sorted_gather<<<blocks_for(n, 256), 256, 0, st>>>(geo, ctx->key2.as<uint32_t>(), ctx->val2.as<uint32_t>(), n,
+        pdl(k_sorted_gather, blocks_for(n, 256), 256, 0, st)(geo, ctx->key2.as<uint32_t>(), ctx->val2.as<uint32_t>(), n,
                                                              ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                              ctx->sp2.as<float4>(), ctx->sp3.as<float4>(),
                                                              ctx->sflag.as<uint8_t>(), ctx->cell_start.as<uint32_t>());
@@ -499,7 +539,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->ptab, np * 8));
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
-        k_ptab<<<blocks_for(np, 256), 256, 0, st>>>(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
+        pdl(k_ptab, blocks_for(np, 256), 256, 0, st)(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
                                                      RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
@@ -537,7 +577,13 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.counters = d_counters;
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
             if (my_np > 0) {
-                k_gate<<<(unsigned)std::min<int64_t>(blocks_for((my_np + GATE_TB - 1) / GATE_TB, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st>>>(A);
+                // ticket size: GATE_TB parents amortise the ticket/pool atomics on big levels; on small levels
+                // (fewer parents than a few per resident warp) one parent per ticket keeps every warp busy and
+                // the per-warp chain of dependent loads short
+                const int64_t resident_warps = (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS * GATE_WARPS;
+                A.tb = (int)std::max<int64_t>(1, std::min<int64_t>(GATE_TB, my_np / (2 * resident_warps)));
+                if (g_gate_tb > 0) A.tb = std::min(g_gate_tb, GATE_TB);
+                pdl(k_gate, (unsigned)std::min<int64_t>(blocks_for((my_np + A.tb - 1) / A.tb, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st)(A);
                 CK(cudaGetLastError());
                 ctx->n_launches++;
             }
@@ -549,7 +595,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 }));
             }
             if (fast) break;
-            k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+            pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));                              // sync B
             memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
@@ -594,7 +640,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (G == 1) {
             if (fast || nchunks > 0) {
                 const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
-                k_chunk_copy<<<blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st>>>(
+                pdl(k_chunk_copy, blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), ctx->ptab.as<uint2>(), d_cnt_c,
                     fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P);
@@ -607,7 +653,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             for (int q = 0; q < G; ++q) M = std::max(M, pb[q + 1] - pb[q]);
             CKR(ensure(ctx, ctx->csr_pad, (size_t)std::max<int64_t>(M, 1) * G * 8));
             if (nchunks > 0) {
-                k_chunk_copy<<<blocks_for((int64_t)nchunks * 32, 256), 256, 0, st>>>(
+                pdl(k_chunk_copy, blocks_for((int64_t)nchunks * 32, 256), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>(),
                     nullptr, nullptr, nullptr, nullptr, 0ull);
@@ -642,12 +688,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         }
         if (P > 0 && use_claims) {
             if (!fuse_claims) {
-                k_claims<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                pdl(k_claims, blocks_for(np * 32, 256), 256, 0, st)(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
                                                                     ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
                                                                     ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
-            k_sumlw_claims<<<blocks_for(n, 256), 256, 0, st>>>(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
+            pdl(k_sumlw_claims, blocks_for(n, 256), 256, 0, st)(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
                                                                 ctx->sumlw_mode == 2 ? ~0ull : 4096ull, n, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         } else if (P > 0) {
@@ -680,7 +726,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
-            k_moments<<<(unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st>>>(M);
+            pdl(k_moments, (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st)(M);
             CK(cudaGetLastError());
             ctx->n_launches++;
         }
@@ -709,17 +755,17 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
         return cub::DeviceScan::ExclusiveSum(t, b, it, ctx->orank.as<uint32_t>(), (int)n, st);
     }));
-    k_orphans<<<blocks_for(n, 256), 256, 0, st>>>(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
+    pdl(k_orphans, blocks_for(n, 256), 256, 0, st)(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
                                                    (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
     CK(cudaGetLastError()); ctx->n_launches++;
     // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
-    k_finish<<<blocks_for(cap_rows, 256), 256, 0, st>>>(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
+    pdl(k_finish, blocks_for(cap_rows, 256), 256, 0, st)(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
                                                          ctx->seed, rng_base, pp, distance_delta, ctx->valid.as<uint8_t>(),
                                                          RAD_N.as<float>(), SAFE_N.as<uint8_t>(), PFLAG_N.as<uint32_t>(),
                                                          pool_cap_used ? (unsigned long long)pool_cap_used : ~0ull, d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
-    k_publish<<<1, 32, 0, st>>>(d_ctl, ctx->h_ctl_dev);
+    pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
     CK(cudaGetLastError());
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     CK(cudaStreamSynchronize(st));                                      // sync C
@@ -921,6 +967,9 @@ hem_ctx* hem_create(int device, uint64_t seed)
     cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_sh, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_level, cudaEventDisableTiming);
+    if (const char* cs = getenv("HEM_PDL")) g_pdl = atoi(cs) != 0;
+    if (const char* cs = getenv("HEM_GATE_TICKET")) g_gate_tb = atoi(cs);
+    if (const char* cs = getenv("HEM_CELL_OCC")) { double v = atof(cs); if (v >= 0) ctx->cell_occupancy = v; }
     if (const char* cs = getenv("HEM_CELL_SCALE")) { double v = atof(cs); if (v > 0) ctx->cell_scale = v; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
@@ -971,6 +1020,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
+    else if (k == "cell_occupancy") { if (!(value >= 0)) { ctx->err = "cell_occupancy must be >= 0"; return HEM_ERR_INVALID; } ctx->cell_occupancy = value; }
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
     else { ctx->err = "unknown option: " + k; return HEM_ERR_INVALID; }

@@ -22,6 +22,15 @@
 
 namespace hem {
 
+// Programmatic dependent launch (see pdl() in hem_b200.cu): let the next kernel of the stream become
+// resident early, then wait until the previous kernel has completed and its writes are visible.  Must be
+// the first statement of every kernel launched through pdl(); a no-op under an ordinary launch.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------
 // Layouts
 // ---------------------------------------------------------------------------
@@ -73,6 +82,7 @@ struct Ctl {
 // readback would queue behind the bulk level downloads that share the D2H copy engine.
 __global__ void k_publish(const Ctl* __restrict__ d, Ctl* __restrict__ h_mapped)
 {
+    pdl_enter();
     const unsigned* s = reinterpret_cast<const unsigned*>(d);
     unsigned* o = reinterpret_cast<unsigned*>(h_mapped);
     for (unsigned i = threadIdx.x; i < sizeof(Ctl) / 4; i += blockDim.x) o[i] = s[i];
@@ -81,6 +91,7 @@ __global__ void k_publish(const Ctl* __restrict__ d, Ctl* __restrict__ h_mapped)
 // zero-fill by a kernel (a cudaMemsetAsync may be routed through a copy engine and queue behind bulk DMA)
 __global__ void k_zero(uint4* __restrict__ p, size_t n16)
 {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
         p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(256)
 k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* __restrict__ radius,
        uint32_t* __restrict__ pflag, uint8_t* __restrict__ psafe, Ctl* __restrict__ ctl)
 {
+    pdl_enter();
     // * The FP64 closed-form eigenvalue is ~400 instructions and only one component in
     //   hemReduction is a parent: the parents of a 256-component tile are compacted through
     //   shared memory so that the eigen code runs on full warps.
@@ -355,6 +367,7 @@ k_boxhist(const float4* __restrict__ geo, int64_t n, float lox, float loy, float
 __global__ void k_cellkey(const float4* __restrict__ geo, int64_t n, GridP g, uint32_t* __restrict__ key,
                           uint32_t* __restrict__ val)
 {
+    pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 q0 = geo[4 * i];
@@ -371,6 +384,7 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
                                 float4* __restrict__ sp3, uint8_t* __restrict__ sflag,
                                 uint32_t* __restrict__ cell_start)
 {
+    pdl_enter();
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t i = sval[j], key = skey[j];
@@ -427,6 +441,7 @@ struct GateArgs {
     const float4* pinfo;         // [np * PINFO_F4]
     GridP g;
     int t_begin, t_end;          // this rank's slab of parents (cell order)
+    int tb;                      // parents per work ticket (1..GATE_TB)
     float cthr, kthr, decay2;
     float smd_rej;               // smd pre-test threshold 2*kthr + 0.5 (+inf disables it)
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
@@ -451,6 +466,7 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
                        const float4* __restrict__ geo, GridP g, int np, uint2* __restrict__ ptab,
                        float4* __restrict__ pinfo)
 {
+    pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= np) return;
     const uint32_t pj = psorted[t];
@@ -479,6 +495,7 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
 __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
 k_gate(GateArgs A)
 {
+    pdl_enter();
     __shared__ uint32_t s_q[GATE_WARPS][64];
     __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
     __shared__ uint2 s_q2[GATE_WARPS][64];
@@ -493,13 +510,13 @@ k_gate(GateArgs A)
     // persistent warps: parents are handed out in cell order through one ticket counter, so
     // neighbouring warps stream the same cell runs and a heavy parent delays nobody else
     for (;;) {
-        // one ticket = GATE_TB consecutive parents: three same-address atomics per parent (ticket,
+        // one ticket = A.tb (<= GATE_TB) consecutive parents: three same-address atomics per parent (ticket,
         // pool, chunk) serialised at the L2 and were 13 % of the kernel's stall samples
         unsigned long long ticket = 0;
         if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
-        const int tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * GATE_TB;
+        const int tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * A.tb;
         if (tfirst >= A.t_end) break;
-        const int tlast = min(tfirst + GATE_TB, A.t_end);
+        const int tlast = min(tfirst + A.tb, A.t_end);
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
@@ -722,6 +739,7 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long lon
                              const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c, uint2* __restrict__ claims,
                              uint4* __restrict__ ovf, unsigned long long ovf_cap)
 {
+    pdl_enter();
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -786,6 +804,7 @@ __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restr
                          uint2* __restrict__ claims, uint4* __restrict__ ovf, unsigned long long ovf_cap,
                          unsigned long long pool_cap, unsigned long long* __restrict__ counters)
 {
+    pdl_enter();
     if (pool_overflowed(counters, pool_cap)) return;
     const int lane = threadIdx.x & 31;
     const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -808,6 +827,7 @@ __global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* 
                                const uint4* __restrict__ ovf, unsigned long long* __restrict__ counters,
                                unsigned long long ovf_limit, int64_t n, float* __restrict__ sumlw)
 {
+    pdl_enter();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const uint32_t m = cnt_c[c];
@@ -903,6 +923,7 @@ struct MomArgs {
 __global__ void __launch_bounds__(MOM_WARPS * 32)
 k_moments(MomArgs A)
 {
+    pdl_enter();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int Fp = A.Fp;
@@ -1026,6 +1047,7 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
           const float* __restrict__ sumlw, const uint32_t* __restrict__ orank, uint32_t np,
           float4* __restrict__ ogeo, float* __restrict__ osh)
 {
+    pdl_enter();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
@@ -1060,6 +1082,7 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
          float* __restrict__ radius_n, uint8_t* __restrict__ psafe_n, uint32_t* __restrict__ pflag_n,
          unsigned long long pool_cap, Ctl* __restrict__ ctl)
 {
+    pdl_enter();
     __shared__ unsigned int s_red[8][10];
     __shared__ unsigned long long s_redd[8];
     if (pool_overflowed(ctl->counters, pool_cap)) return;     // merged rows were not produced: the host redoes the step
