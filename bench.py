@@ -305,14 +305,14 @@ def run_b200_arm(a, rank, local_rank, world):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (level-0 launch of this
     # very workload); bench.py itself never runs under a profiler
     traffic, traffic_note = None, None
-    prof = os.path.join(ROOT, "profiles", "r01_v5_ncu_full_hot_kernels.csv")
+    prof = os.path.join(ROOT, "profiles", "r01_v6_ncu_full_hot_kernels.csv")
     if os.path.exists(prof) and a.n == 1_000_000:
         import csv
         rows = {r[0]: r for r in csv.reader(open(prof)) if r}
         try:
             traffic = (float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])) * 1e6
             l0 = stats[0]
-            traffic_note = ("ncu --set full, level-0 k_gate launch (profiles/r01_v5_ncu_full_hot_kernels.csv); algorithmic bytes "
+            traffic_note = ("ncu --set full, level-0 k_gate launch (profiles/r01_v6_ncu_full_hot_kernels.csv); algorithmic bytes "
                             f"of that launch = {(64 * l0['n_in'] + 60 * l0['n_parents'] + 12 * l0['n_pairs']) / 1e6:.1f} MB")
         except (KeyError, ValueError, IndexError):
             traffic = None
