@@ -357,6 +357,32 @@ def test_gpu_parameter_sweep_vs_oracle(port, red, dd, cd, decay, deg):
                              params=dict(hem_reduction=red, distance_delta=dd, color_delta=cd, decay_rate=decay))
 
 
+@pytest.mark.parametrize("n,red,dd,cd,decay,deg", [
+    (12000, 1.0, 3.0, 2.5, 1.0, 1),       # every component is a parent: parent exclusion leaves each with itself only
+    (12000, 50.0, 3.0, 2.5, 1.0, 1),      # very few parents, almost everything is an orphan
+    (12000, 3.0, 0.05, 2.5, 1.0, 0),      # radius far below the spacing
+    (6000, 3.0, 12.0, 50.0, 1.0, 0),      # radius of many spacings: hundreds of children per parent
+    (3000, 3.0, 150.0, 1e3, 1.0, 1),      # KLD threshold above 1e4 (pre-test disabled by rule), every pair a candidate
+    (12000, 3.0, 3.0, 0.0, 1.0, 1),       # colour gate at zero
+    (12000, 3.0, 3.0, 2.5, 0.01, 1),      # decay so small that the likelihood underflows into the FLT_MIN clamp
+    (12000, 3.0, 3.0, 2.5, 1e4, 1),       # decay so large that both exponentials are 1
+])
+def test_gpu_extreme_parameters_vs_oracle(port, n, red, dd, cd, decay, deg):
+    """CreateMixture arguments at the ends of what the reference accepts (its UI bounds are wider still)."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(n, seed=int(n / 100 + red + dd), density=8000.0, sh_degree=deg)
+    with HemContext(0, seed=21) as ctx:
+        ctx.set_option("keep_pairs", 1)
+        ctx.build(*c.arrays(), cluster_level=2, hem_reduction=red, distance_delta=dd, color_delta=cd, decay_rate=decay)
+        r = port.run(*c.arrays(), 2, red, dd, cd, decay, seed=21)
+
+        def children(l):
+            ch = r.children(l)
+            return ch["parent_idx"], ch["off"], ch["child"]
+        compare_free_running(ctx, r.level, children, 2, f"n={n} red={red} dd={dd} cd={cd} decay={decay}", port_run=r,
+                             params=dict(hem_reduction=red, distance_delta=dd, color_delta=cd, decay_rate=decay))
+
+
 @pytest.mark.parametrize("case", ["offset", "duplicates", "planar", "tiny"])
 def test_gpu_awkward_geometry_vs_oracle(port, case):
     """Inputs that stress the grid: a cloud far from the origin (FP32 cell arithmetic), coincident
