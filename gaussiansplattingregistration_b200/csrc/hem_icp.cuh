@@ -16,10 +16,10 @@
 // GPU formulation: the target cloud is binned once into a uniform grid (linear cell key, radix sort,
 // cell-start table); each source thread walks Chebyshev shells of cells outwards until the best hit is
 // provably the nearest (best <= (shell * cell)^2) or the search radius is covered.  All FP64.  One
-// iteration = one k_icp_nn launch (fixed grid, per-block partial sums in a fixed order -> deterministic)
-// + one single-block k_icp_update that reduces the partials, tests convergence and computes the rigid
-// update with Horn's quaternion method (Jacobi on the 4x4 symmetric matrix), all on the device: the host
-// enqueues every iteration up front and synchronises once; iterations after convergence exit at once.
+// iteration = ONE k_icp_nn launch (fixed grid, per-block partial sums in a fixed order -> deterministic);
+// its last block to finish reduces the partials, tests convergence and computes the rigid update with
+// Horn's quaternion method (Jacobi on the 4x4 symmetric matrix), all on the device: the host enqueues
+// every iteration up front and synchronises once; iterations after convergence exit at once.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -67,7 +67,7 @@ __host__ __device__ __forceinline__ double dec_ordered(unsigned long long e)
 }
 
 // bounding box of the finite points: box[0..2] = min (ordered encoding), box[3..5] = max
-__global__ void k_icp_bbox(const double* __restrict__ p, int64_t n, unsigned long long* __restrict__ box)
+__global__ void __launch_bounds__(256) k_icp_bbox(const double* __restrict__ p, int64_t n, unsigned long long* __restrict__ box)
 {
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -78,6 +78,7 @@ __global__ void k_icp_bbox(const double* __restrict__ p, int64_t n, unsigned lon
             lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
         }
     }
+    __shared__ double s_lo[8][3], s_hi[8][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         for (int o = 16; o; o >>= 1) {
@@ -86,10 +87,14 @@ __global__ void k_icp_bbox(const double* __restrict__ p, int64_t n, unsigned lon
         }
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&box[k], enc_ordered(lo[k]));
-            atomicMax(&box[3 + k], enc_ordered(hi[k]));
-        }
+        for (int k = 0; k < 3; ++k) { s_lo[threadIdx.x >> 5][k] = lo[k]; s_hi[threadIdx.x >> 5][k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = s_lo[0][threadIdx.x], b = s_hi[0][threadIdx.x];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fmin(a, s_lo[w][threadIdx.x]); b = fmax(b, s_hi[w][threadIdx.x]); }
+        atomicMin(&box[threadIdx.x], enc_ordered(a));
+        atomicMax(&box[3 + threadIdx.x], enc_ordered(b));
+    }
 }
 
 __device__ __forceinline__ int cell_of(double v, double lo, double inv_h, int g)
@@ -132,9 +137,10 @@ __global__ void k_icp_gather(const double* __restrict__ p, const uint32_t* __res
         for (uint32_t c = k + 1; c <= ncell; ++c) start[c] = (uint32_t)n;
 }
 
-__global__ void k_icp_init(State* __restrict__ st, Mat16 init)
+__global__ void k_icp_init(State* __restrict__ st, Mat16 init, unsigned int* __restrict__ block_counter)
 {
     if (threadIdx.x || blockIdx.x) return;
+    *block_counter = 0u;
     for (int k = 0; k < 16; ++k) st->T[k] = init.m[k];
     st->fitness = st->rmse = st->prev_fitness = st->prev_rmse = 0.0;
     st->n_corr = 0;
@@ -142,6 +148,136 @@ __global__ void k_icp_init(State* __restrict__ st, Mat16 init)
     st->done = 0;
     st->evals = 0;
     st->pad = 0;
+}
+
+
+// largest-eigenvalue eigenvector of a symmetric 4x4 matrix by cyclic Jacobi rotations (FP64)
+__host__ __device__ inline void jacobi4_max_eigvec(double A[4][4], double q[4])
+{
+    double V[4][4] = { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 }, { 0, 0, 0, 1 } };
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;   // eigenvector error ~ sqrt(off)/gap: at FP64 rounding level
+        for (int p = 0; p < 3; ++p)
+            for (int r = p + 1; r < 4; ++r) {
+                const double apq = A[p][r];
+                if (apq == 0.0) continue;
+                const double theta = (A[r][r] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 4; ++k) {
+                    const double akp = A[k][p], akq = A[k][r];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][r] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const double apk = A[p][k], aqk = A[r][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[r][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][r];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][r] = s * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 4; ++i)
+        if (A[i][i] > A[best][best]) best = i;
+    double n2 = 0.0;
+    for (int k = 0; k < 4; ++k) { q[k] = V[k][best]; n2 += q[k] * q[k]; }
+    const double inv = 1.0 / sqrt(n2);
+    for (int k = 0; k < 4; ++k) q[k] *= inv;
+}
+
+// Reduce the partial sums (fixed order), close the evaluation (fitness, rmse, convergence test) and,
+// if the loop goes on, compute the rigid update and apply it to T.  Runs in the LAST block of k_icp_nn to
+// finish (the order of the reduction does not depend on which block that is).
+struct UpdateArgs {
+    double rel_fitness, rel_rmse;
+    int max_iteration;
+    unsigned int* block_counter;     // zero before the first launch; the last block resets it
+    State* host_copy;                // mapped host memory
+};
+
+__device__ __forceinline__ void icp_update(const double* __restrict__ partials, int nparts, int64_t ns, const UpdateArgs& U,
+                                           double ox, double oy, double oz, State* __restrict__ st,
+                                           double (*sm)[NSUM + 1])
+{
+    double acc[NSUM];
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
+    for (int b = threadIdx.x; b < nparts; b += NN_THREADS)
+#pragma unroll
+        for (int k = 0; k < NSUM; ++k) acc[k] += __ldcg(&partials[(size_t)b * NSUM + k]);
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) sm[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (int o = NN_THREADS / 2; o; o >>= 1) {
+        if ((int)threadIdx.x < o)
+#pragma unroll
+            for (int k = 0; k < NSUM; ++k) sm[threadIdx.x][k] += sm[threadIdx.x + o][k];
+        __syncthreads();
+    }
+    const double rel_fitness = U.rel_fitness, rel_rmse = U.rel_rmse;
+    const int max_iteration = U.max_iteration;
+    State* host_copy = U.host_copy;
+    if (threadIdx.x) return;
+    const double* S = sm[0];
+    const double n = S[0];
+    const double fitness = ns > 0 ? n / (double)ns : 0.0;
+    const double rmse = n > 0.0 ? sqrt(S[1] / n) : 0.0;
+    const int it = st->iter;
+    const bool conv = it > 0 && fabs(st->prev_fitness - fitness) < rel_fitness && fabs(st->prev_rmse - rmse) < rel_rmse;
+    st->fitness = fitness;
+    st->rmse = rmse;
+    st->n_corr = (long long)n;
+    st->evals += 1;
+    if (conv) st->done = 1;
+    else if (it >= max_iteration) st->done = 2;
+    else if (n < 3.0) st->done = 3;
+    else {
+        const double inv = 1.0 / n;
+        const double ca[3] = { S[2] * inv, S[3] * inv, S[4] * inv }, cb[3] = { S[5] * inv, S[6] * inv, S[7] * inv };
+        double H[3][3];   // H[i][j] = mean (a_i - ca_i)(b_j - cb_j)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) H[i][j] = S[8 + 3 * i + j] * inv - ca[i] * cb[j];
+        // Horn 1987: the rotation maximising sum b . (R a) is the top eigenvector of N(H)
+        double N[4][4] = {
+            { H[0][0] + H[1][1] + H[2][2], H[1][2] - H[2][1], H[2][0] - H[0][2], H[0][1] - H[1][0] },
+            { H[1][2] - H[2][1], H[0][0] - H[1][1] - H[2][2], H[0][1] + H[1][0], H[2][0] + H[0][2] },
+            { H[2][0] - H[0][2], H[0][1] + H[1][0], -H[0][0] + H[1][1] - H[2][2], H[1][2] + H[2][1] },
+            { H[0][1] - H[1][0], H[2][0] + H[0][2], H[1][2] + H[2][1], -H[0][0] - H[1][1] + H[2][2] } };
+        double q[4];
+        jacobi4_max_eigvec(N, q);
+        const double w = q[0], x = q[1], y = q[2], z = q[3];
+        const double R[3][3] = { { 1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - w * z), 2.0 * (x * z + w * y) },
+                                 { 2.0 * (x * y + w * z), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - w * x) },
+                                 { 2.0 * (x * z - w * y), 2.0 * (y * z + w * x), 1.0 - 2.0 * (x * x + y * y) } };
+        // b - o = R (a - o) + t'  ->  b = R a + (t' + o - R o)
+        const double o[3] = { ox, oy, oz };
+        double t[3];
+        for (int i = 0; i < 3; ++i) {
+            const double tp = cb[i] - (R[i][0] * ca[0] + R[i][1] * ca[1] + R[i][2] * ca[2]);
+            t[i] = tp + o[i] - (R[i][0] * o[0] + R[i][1] * o[1] + R[i][2] * o[2]);
+        }
+        double Tn[16];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 4; ++j)
+                Tn[4 * i + j] = R[i][0] * st->T[j] + R[i][1] * st->T[4 + j] + R[i][2] * st->T[8 + j] + (j == 3 ? t[i] : 0.0);
+        }
+        Tn[12] = 0.0; Tn[13] = 0.0; Tn[14] = 0.0; Tn[15] = 1.0;
+        for (int k = 0; k < 16; ++k) st->T[k] = Tn[k];
+        st->prev_fitness = fitness;
+        st->prev_rmse = rmse;
+        st->iter = it + 1;
+    }
+    if (host_copy) *host_copy = *st;
 }
 
 __device__ __forceinline__ void scan_range(const double4* __restrict__ rows, uint32_t s, uint32_t e, double px,
@@ -161,7 +297,7 @@ __device__ __forceinline__ void scan_range(const double4* __restrict__ rows, uin
 __global__ void __launch_bounds__(NN_THREADS)
 k_icp_nn(const double* __restrict__ src, int64_t ns, const double4* __restrict__ rows,
          const uint32_t* __restrict__ start, Grid g, double max_corr, double ox, double oy, double oz,
-         const State* __restrict__ st, double* __restrict__ partials, int32_t* __restrict__ corr)
+         State* __restrict__ st, double* __restrict__ partials, int32_t* __restrict__ corr, UpdateArgs U)
 {
     if (st->done) return;
     double T[12];
@@ -218,7 +354,8 @@ k_icp_nn(const double* __restrict__ src, int64_t ns, const double4* __restrict__
             acc[14] += az * bx; acc[15] += az * by; acc[16] += az * bz;
         }
     }
-    __shared__ double sm[NN_THREADS / 32][NSUM];
+    __shared__ double sm[NN_THREADS][NSUM + 1];
+    __shared__ bool s_last;
 #pragma unroll
     for (int k = 0; k < NSUM; ++k)
         for (int o = 16; o; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
@@ -230,128 +367,20 @@ k_icp_nn(const double* __restrict__ src, int64_t ns, const double4* __restrict__
     if (threadIdx.x < NSUM) {
         double s = 0.0;
         for (int q = 0; q < NN_THREADS / 32; ++q) s += sm[q][threadIdx.x];
-        partials[(size_t)blockIdx.x * NSUM + threadIdx.x] = s;
+        __stcg(&partials[(size_t)blockIdx.x * NSUM + threadIdx.x], s);
     }
-}
-
-// largest-eigenvalue eigenvector of a symmetric 4x4 matrix by cyclic Jacobi rotations (FP64)
-__host__ __device__ inline void jacobi4_max_eigvec(double A[4][4], double q[4])
-{
-    double V[4][4] = { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 }, { 0, 0, 0, 1 } };
-    for (int sweep = 0; sweep < 64; ++sweep) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < 4; ++i) {
-            diag += A[i][i] * A[i][i];
-            for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
-        }
-        if (off <= 1e-34 * (diag + off) || off == 0.0) break;
-        for (int p = 0; p < 3; ++p)
-            for (int r = p + 1; r < 4; ++r) {
-                const double apq = A[p][r];
-                if (apq == 0.0) continue;
-                const double theta = (A[r][r] - A[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 4; ++k) {
-                    const double akp = A[k][p], akq = A[k][r];
-                    A[k][p] = c * akp - s * akq;
-                    A[k][r] = s * akp + c * akq;
-                }
-                for (int k = 0; k < 4; ++k) {
-                    const double apk = A[p][k], aqk = A[r][k];
-                    A[p][k] = c * apk - s * aqk;
-                    A[r][k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 4; ++k) {
-                    const double vkp = V[k][p], vkq = V[k][r];
-                    V[k][p] = c * vkp - s * vkq;
-                    V[k][r] = s * vkp + c * vkq;
-                }
-            }
-    }
-    int best = 0;
-    for (int i = 1; i < 4; ++i)
-        if (A[i][i] > A[best][best]) best = i;
-    double n2 = 0.0;
-    for (int k = 0; k < 4; ++k) { q[k] = V[k][best]; n2 += q[k] * q[k]; }
-    const double inv = 1.0 / sqrt(n2);
-    for (int k = 0; k < 4; ++k) q[k] *= inv;
-}
-
-// Reduce the partial sums (fixed order), close the evaluation (fitness, rmse, convergence test) and,
-// if the loop goes on, compute the rigid update and apply it to T.
-__global__ void __launch_bounds__(256)
-k_icp_update(const double* __restrict__ partials, int nparts, int64_t ns, double rel_fitness, double rel_rmse,
-             int max_iteration, double ox, double oy, double oz, State* __restrict__ st, State* __restrict__ host_copy)
-{
-    if (st->done) return;
-    __shared__ double sm[256][NSUM + 1];
-    double acc[NSUM];
-#pragma unroll
-    for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
-    for (int b = threadIdx.x; b < nparts; b += 256)
-#pragma unroll
-        for (int k = 0; k < NSUM; ++k) acc[k] += partials[(size_t)b * NSUM + k];
-#pragma unroll
-    for (int k = 0; k < NSUM; ++k) sm[threadIdx.x][k] = acc[k];
+    // last block to finish closes the evaluation (threadfence-reduction pattern)
+    __threadfence();
     __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if ((int)threadIdx.x < o)
-#pragma unroll
-            for (int k = 0; k < NSUM; ++k) sm[threadIdx.x][k] += sm[threadIdx.x + o][k];
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done_blocks = atomicAdd(U.block_counter, 1u);
+        s_last = (done_blocks == gridDim.x - 1);
     }
-    if (threadIdx.x) return;
-    const double* S = sm[0];
-    const double n = S[0];
-    const double fitness = ns > 0 ? n / (double)ns : 0.0;
-    const double rmse = n > 0.0 ? sqrt(S[1] / n) : 0.0;
-    const int it = st->iter;
-    const bool conv = it > 0 && fabs(st->prev_fitness - fitness) < rel_fitness && fabs(st->prev_rmse - rmse) < rel_rmse;
-    st->fitness = fitness;
-    st->rmse = rmse;
-    st->n_corr = (long long)n;
-    st->evals += 1;
-    if (conv) st->done = 1;
-    else if (it >= max_iteration) st->done = 2;
-    else if (n < 3.0) st->done = 3;
-    else {
-        const double inv = 1.0 / n;
-        const double ca[3] = { S[2] * inv, S[3] * inv, S[4] * inv }, cb[3] = { S[5] * inv, S[6] * inv, S[7] * inv };
-        double H[3][3];   // H[i][j] = mean (a_i - ca_i)(b_j - cb_j)
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) H[i][j] = S[8 + 3 * i + j] * inv - ca[i] * cb[j];
-        // Horn 1987: the rotation maximising sum b . (R a) is the top eigenvector of N(H)
-        double N[4][4] = {
-            { H[0][0] + H[1][1] + H[2][2], H[1][2] - H[2][1], H[2][0] - H[0][2], H[0][1] - H[1][0] },
-            { H[1][2] - H[2][1], H[0][0] - H[1][1] - H[2][2], H[0][1] + H[1][0], H[2][0] + H[0][2] },
-            { H[2][0] - H[0][2], H[0][1] + H[1][0], -H[0][0] + H[1][1] - H[2][2], H[1][2] + H[2][1] },
-            { H[0][1] - H[1][0], H[2][0] + H[0][2], H[1][2] + H[2][1], -H[0][0] - H[1][1] + H[2][2] } };
-        double q[4];
-        jacobi4_max_eigvec(N, q);
-        const double w = q[0], x = q[1], y = q[2], z = q[3];
-        const double R[3][3] = { { 1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - w * z), 2.0 * (x * z + w * y) },
-                                 { 2.0 * (x * y + w * z), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - w * x) },
-                                 { 2.0 * (x * z - w * y), 2.0 * (y * z + w * x), 1.0 - 2.0 * (x * x + y * y) } };
-        // b - o = R (a - o) + t'  ->  b = R a + (t' + o - R o)
-        const double o[3] = { ox, oy, oz };
-        double t[3];
-        for (int i = 0; i < 3; ++i) {
-            const double tp = cb[i] - (R[i][0] * ca[0] + R[i][1] * ca[1] + R[i][2] * ca[2]);
-            t[i] = tp + o[i] - (R[i][0] * o[0] + R[i][1] * o[1] + R[i][2] * o[2]);
-        }
-        double Tn[16];
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 4; ++j)
-                Tn[4 * i + j] = R[i][0] * st->T[j] + R[i][1] * st->T[4 + j] + R[i][2] * st->T[8 + j] + (j == 3 ? t[i] : 0.0);
-        }
-        Tn[12] = 0.0; Tn[13] = 0.0; Tn[14] = 0.0; Tn[15] = 1.0;
-        for (int k = 0; k < 16; ++k) st->T[k] = Tn[k];
-        st->prev_fitness = fitness;
-        st->prev_rmse = rmse;
-        st->iter = it + 1;
-    }
-    if (host_copy) *host_copy = *st;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    icp_update(partials, (int)gridDim.x, ns, U, ox, oy, oz, st, sm);
+    if (threadIdx.x == 0) *U.block_counter = 0u;
 }
 
 } // namespace icp

@@ -100,21 +100,23 @@ int icp_run(hem_ctx* ctx, const double* d_src, int64_t ns, const double* d_tgt, 
     // ---- iterations, all enqueued up front; the device decides when to stop -------------------
     const int nblocks = (int)std::min<int64_t>((ns + NN_THREADS - 1) / NN_THREADS, (int64_t)ctx->sm_count * 16);
     CKR(ensure(ctx, ctx->icp_part, (size_t)nblocks * NSUM * sizeof(double)));
-    CKR(ensure(ctx, ctx->icp_state, sizeof(State)));
+    CKR(ensure(ctx, ctx->icp_state, sizeof(State) + 16));
     int32_t* d_corr = nullptr;
     if (correspondence) {
         if (is_device_ptr(correspondence)) d_corr = correspondence;
         else { CKR(ensure(ctx, ctx->icp_corr, (size_t)ns * 4)); d_corr = ctx->icp_corr.as<int32_t>(); }
     }
     State* dst = ctx->icp_state.as<State>();
-    k_icp_init<<<1, 32, 0, st>>>(dst, T0);
+    UpdateArgs U;
+    U.rel_fitness = P.rel_fitness; U.rel_rmse = P.rel_rmse; U.max_iteration = P.max_iteration;
+    U.block_counter = (unsigned int*)(ctx->icp_state.as<char>() + sizeof(State));
+    U.host_copy = ctx->h_icp_dev;
+    k_icp_init<<<1, 32, 0, st>>>(dst, T0, U.block_counter);
     CK(cudaGetLastError()); ctx->n_launches++;
     for (int k = 0; k <= P.max_iteration; ++k) {
         k_icp_nn<<<nblocks, NN_THREADS, 0, st>>>(d_src, ns, ctx->icp_rows.as<double4>(), ctx->icp_start.as<uint32_t>(), g, P.max_corr,
-                                                 ox, oy, oz, dst, ctx->icp_part.as<double>(), d_corr);
-        k_icp_update<<<1, 256, 0, st>>>(ctx->icp_part.as<double>(), nblocks, ns, P.rel_fitness, P.rel_rmse, P.max_iteration, ox, oy,
-                                        oz, dst, ctx->h_icp_dev);
-        ctx->n_launches += 2;
+                                                 ox, oy, oz, dst, ctx->icp_part.as<double>(), d_corr, U);
+        ctx->n_launches++;
     }
     CK(cudaGetLastError());
     if (correspondence && d_corr != correspondence) {
