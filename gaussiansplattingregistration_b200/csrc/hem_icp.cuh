@@ -280,6 +280,14 @@ __device__ __forceinline__ void icp_update(const double* __restrict__ partials, 
     if (host_copy) *host_copy = *st;
 }
 
+// distance from coordinate q to the slab of cell c along one axis (0 inside; a hair of slack for the
+// rounding of the cell assignment)
+__device__ __forceinline__ double slab_dist(double q, double lo, double h, int c)
+{
+    const double a = lo + (double)c * h;
+    return fmax(0.0, fmax(a - q, q - (a + h)) - 1e-9 * h);
+}
+
 __device__ __forceinline__ void scan_range(const double4* __restrict__ rows, uint32_t s, uint32_t e, double px,
                                            double py, double pz, double& best, double4& hit)
 {
@@ -324,14 +332,29 @@ k_icp_nn(const double* __restrict__ src, int64_t ns, const double4* __restrict__
                 const int xa = max(x0, 0), xb = min(x1, g.g[0] - 1);
                 for (int z = max(z0, 0); z <= min(z1, g.g[2] - 1); ++z) {
                     const bool zedge = (z == z0) || (z == z1);
+                    const double dz = slab_dist(pz, g.lo[2], g.h, z);
+                    if (dz * dz >= best) continue;
                     for (int y = max(y0, 0); y <= min(y1, g.g[1] - 1); ++y) {
+                        // rows of cells the current best sphere misses are skipped, the others trimmed to its chord
+                        const double dy = slab_dist(py, g.lo[1], g.h, y);
+                        const double rem = best - (dz * dz + dy * dy);
+                        if (rem <= 0.0) continue;
                         const uint32_t base = (uint32_t)g.g[0] * ((uint32_t)y + (uint32_t)g.g[1] * (uint32_t)z);
                         if (zedge || y == y0 || y == y1) {
                             // a whole x-run of the shell: consecutive keys, one contiguous range of rows
-                            scan_range(rows, start[base + xa], start[base + xb + 1], px, py, pz, best, hit);
+                            const double half = sqrt(rem) + 1e-9 * g.h;
+                            const int ca = max(xa, cell_of(px - half, g.lo[0], g.inv_h, g.g[0]));
+                            const int cb = min(xb, cell_of(px + half, g.lo[0], g.inv_h, g.g[0]));
+                            if (ca <= cb) scan_range(rows, start[base + ca], start[base + cb + 1], px, py, pz, best, hit);
                         } else {
-                            if (x0 >= 0) scan_range(rows, start[base + x0], start[base + x0 + 1], px, py, pz, best, hit);
-                            if (x1 < g.g[0]) scan_range(rows, start[base + x1], start[base + x1 + 1], px, py, pz, best, hit);
+                            if (x0 >= 0) {
+                                const double dx = slab_dist(px, g.lo[0], g.h, x0);
+                                if (dx * dx < rem) scan_range(rows, start[base + x0], start[base + x0 + 1], px, py, pz, best, hit);
+                            }
+                            if (x1 < g.g[0]) {
+                                const double dx = slab_dist(px, g.lo[0], g.h, x1);
+                                if (dx * dx < rem) scan_range(rows, start[base + x1], start[base + x1 + 1], px, py, pz, best, hit);
+                            }
                         }
                     }
                 }
