@@ -261,8 +261,10 @@ def run_b200_arm(a, rank, local_rank, world):
     F = cloud.sh_floats
     # one pinned destination per returned level (what CreateMixture hands back), bound once: each level
     # is copied out on the library's copy stream while the next one is being built
+    # Under torchrun the pyramid is returned to ONE caller: rank 0 binds the destinations, the other ranks are
+    # workers (each uploads 1/N of the host arrays over its own PCIe link, the slices are all-gathered over NVLink).
     outb = []
-    for l in range(1, a.levels + 1):
+    for l in range(1, a.levels + 1 if rank == 0 else 1):
         cap = int(sizes[l] * 1.02) + 1024
         bufs = [torch.empty((cap, 3), dtype=torch.float32).pin_memory(), torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
                 torch.empty(cap, dtype=torch.float32).pin_memory(), torch.empty((cap, 6), dtype=torch.float32).pin_memory(),
@@ -288,11 +290,14 @@ def run_b200_arm(a, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = sum_n * k_e2e / (e2e_ms / 1e3)
-    h2d = (ctx.info("bytes_h2d") - h0) / k_e2e
-    d2h = (ctx.info("bytes_d2h") - d0) / k_e2e
+    io = torch.tensor([ctx.info("bytes_h2d") - h0, ctx.info("bytes_d2h") - d0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)          # bytes over all ranks' PCIe links
+    h2d, d2h = float(io[0].item()) / k_e2e, float(io[1].item()) / k_e2e
     # the bound host buffers now hold the last pyramid: spot-check them against a plain readback
-    chk = ctx.level(1)
-    assert np.array_equal(outb[0][0].numpy()[:sizes[1]], chk["xyz"]) and np.array_equal(outb[0][4].numpy()[:sizes[1]], chk["sh"])
+    if rank == 0:
+        chk = ctx.level(1)
+        assert np.array_equal(outb[0][0].numpy()[:sizes[1]], chk["xyz"]) and np.array_equal(outb[0][4].numpy()[:sizes[1]], chk["sh"])
     ctx.clear_outputs()
 
     if rank != 0:

@@ -106,6 +106,10 @@ struct hem_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_geo = nullptr, ev_sh = nullptr, ev_level = nullptr;
     bool sh_pending = false;                     // level-0 SH H2D still in flight on copy_stream
+    int64_t sh_gather_chunk = 0;                 // > 0: only this rank's slice of the SH rows was uploaded; all-gather after the wait
+    float* sh_gather_buf = nullptr;
+    int sh_gather_row = 0;
+    bool shard_upload = true;                    // multi-GPU: upload 1/world of a host input per rank + all-gather
     struct OutBind { float *xyz = nullptr, *color = nullptr, *opacity = nullptr, *cov6 = nullptr, *sh = nullptr; int64_t cap = 0; bool set = false; };
     std::vector<OutBind> binds;
 
@@ -210,6 +214,31 @@ template <class... KArgs> PdlLaunch<KArgs...> pdl(void (*kernel)(KArgs...), dim3
     return L;
 }
 
+int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk);
+
+// Multi-GPU build from HOST arrays: every rank uploads only its 1/world slice of the rows over its own
+// PCIe link and the ranks all-gather the slices over NVLink (the alternative — every rank uploading the
+// whole cloud — multiplies the host-side traffic by the number of GPUs).  Every rank must pass the same
+// kind of pointer (host or device) for the same argument, as it must pass the same values.
+int to_device_sharded(hem_ctx* ctx, const void* src, int64_t rows, size_t row_bytes, DevBuf& stage, const void** out)
+{
+    if (!src) { *out = nullptr; return HEM_OK; }
+    if (is_device_ptr(src)) { *out = src; return HEM_OK; }
+    if (ctx->world <= 1 || !ctx->shard_upload)
+        return to_device(ctx, src, (size_t)rows * row_bytes, stage, out);
+    const int64_t chunk = (rows + ctx->world - 1) / ctx->world;
+    CKR(ensure(ctx, stage, (size_t)chunk * ctx->world * row_bytes));
+    const int64_t b = std::min<int64_t>(chunk * ctx->rank, rows), e = std::min<int64_t>(b + chunk, rows);
+    if (e > b) {
+        CK(cudaMemcpyAsync((char*)stage.p + (size_t)b * row_bytes, (const char*)src + (size_t)b * row_bytes,
+                           (size_t)(e - b) * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->bytes_h2d += (size_t)(e - b) * row_bytes;
+    }
+    CKR(allgather_equal(ctx, stage.p, row_bytes, chunk));
+    *out = stage.p;
+    return HEM_OK;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
 int bits_for(uint64_t max_value)
@@ -309,6 +338,18 @@ int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk)
     if (ctx->world <= 1 || chunk <= 0) return HEM_OK;
     const size_t bytes = (size_t)chunk * elem;
     NK(g_nccl.AllGather((char*)buf + (size_t)ctx->rank * bytes, buf, bytes, /*ncclChar*/ 0, ctx->nccl_comm, ctx->stream));
+    return HEM_OK;
+}
+
+// the level-0 SH rows become visible to the main stream (and, after a sharded upload, complete on every rank)
+int wait_sh(hem_ctx* ctx)
+{
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sh, 0));
+    ctx->sh_pending = false;
+    if (ctx->sh_gather_chunk > 0) {
+        CKR(allgather_equal(ctx, ctx->sh_gather_buf, (size_t)ctx->sh_gather_row, ctx->sh_gather_chunk));
+        ctx->sh_gather_chunk = 0;
+    }
     return HEM_OK;
 }
 
@@ -723,7 +764,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->stage_sh, (size_t)slab_chunk(np, G) * G * std::max(Fp, 1) * 4));
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
-        if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
+        if (ctx->sh_pending) CKR(wait_sh(ctx));
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
             pdl(k_moments, (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st)(M);
@@ -749,7 +790,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
 
     // ---- S5 orphans + filter ---------------------------------------------------------------------------
-    if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
+    if (ctx->sh_pending) CKR(wait_sh(ctx));
     CKR(ensure(ctx, ctx->orank, n * 4));
     CKR(cub_call(ctx, [&](void* t, size_t& b) {
         cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
@@ -1020,6 +1061,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
+    else if (k == "shard_upload") ctx->shard_upload = value != 0;
     else if (k == "cell_occupancy") { if (!(value >= 0)) { ctx->err = "cell_occupancy must be >= 0"; return HEM_ERR_INVALID; } ctx->cell_occupancy = value; }
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }
@@ -1055,12 +1097,12 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     L0.n = n;
     if (n > 0) {
         const void *dx, *dc, *dop, *dcv, *dw, *dm;
-        CKR(to_device(ctx, xyz, (size_t)n * 12, ctx->in_xyz, &dx));
-        CKR(to_device(ctx, color, (size_t)n * 12, ctx->in_col, &dc));
-        CKR(to_device(ctx, opacity, (size_t)n * 4, ctx->in_op, &dop));
-        CKR(to_device(ctx, cov6, (size_t)n * 24, ctx->in_cov, &dcv));
-        CKR(to_device(ctx, weight, (size_t)n * 4, ctx->in_w, &dw));
-        CKR(to_device(ctx, level0_parent_mask, (size_t)n, ctx->in_mask, &dm));
+        CKR(to_device_sharded(ctx, xyz, n, 12, ctx->in_xyz, &dx));
+        CKR(to_device_sharded(ctx, color, n, 12, ctx->in_col, &dc));
+        CKR(to_device_sharded(ctx, opacity, n, 4, ctx->in_op, &dop));
+        CKR(to_device_sharded(ctx, cov6, n, 24, ctx->in_cov, &dcv));
+        CKR(to_device_sharded(ctx, weight, n, 4, ctx->in_w, &dw));
+        CKR(to_device_sharded(ctx, level0_parent_mask, n, 1, ctx->in_mask, &dm));
         CKR(ensure(ctx, L0.geo, (size_t)n * 64));
         k_import<<<blocks_for(n, 256), 256, 0, st>>>((const float*)dx, (const float*)dc, (const float*)dop,
                                                       (const float*)dcv, (const float*)dw, (const uint8_t*)dm,
@@ -1071,9 +1113,27 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
         if (Fp > 0 && is_device_ptr(sh)) {
             L0.shp = sh;
         } else {
-            CKR(ensure(ctx, L0.sh, (size_t)n * std::max(Fp, 1) * 4));
+            const bool shard = ctx->world > 1 && ctx->shard_upload && Fp > 0;
+            const int64_t chunk = shard ? (n + ctx->world - 1) / ctx->world : n;
+            CKR(ensure(ctx, L0.sh, (size_t)(shard ? chunk * ctx->world : n) * std::max(Fp, 1) * 4));
             L0.shp = L0.sh.as<float>();
-            if (Fp > 0) {
+            ctx->sh_gather_chunk = 0;
+            if (shard) {
+                // this rank's slice on the copy stream; the all-gather over NVLink follows the wait on the main stream
+                const int64_t b = std::min<int64_t>(chunk * ctx->rank, n), e = std::min<int64_t>(b + chunk, n);
+                CK(cudaEventRecord(ctx->ev_geo, st));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_geo, 0));
+                if (e > b) {
+                    CK(cudaMemcpyAsync(L0.sh.as<float>() + (size_t)b * Fp, sh + (size_t)b * Fp, (size_t)(e - b) * Fp * 4,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+                    ctx->bytes_h2d += (size_t)(e - b) * Fp * 4;
+                }
+                CK(cudaEventRecord(ctx->ev_sh, ctx->copy_stream));
+                ctx->sh_pending = true;
+                ctx->sh_gather_chunk = chunk;
+                ctx->sh_gather_buf = L0.sh.as<float>();
+                ctx->sh_gather_row = Fp * 4;
+            } else if (Fp > 0) {
                 // the SH rows (3/4 of the bytes) are first read by the level-0 moment kernel: their H2D
                 // runs on the copy stream, behind the geometry, under the prep / grid / gate kernels
                 CK(cudaEventRecord(ctx->ev_geo, st));
@@ -1129,7 +1189,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
             }
         }
     }
-    if (ctx->sh_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_sh, 0)); ctx->sh_pending = false; }
+    if (ctx->sh_pending) CKR(wait_sh(ctx));
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }

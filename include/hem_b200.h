@@ -65,6 +65,9 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 ways of adding a child's claims in ascending parent order
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
  *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
+ *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own
+ *                 PCIe link and the slices are all-gathered over NVLink; 0 -> every rank uploads everything
+ *   "cell_occupancy" lower bound of the grid cell edge in units of the mean component spacing (default 1.3; 0 = off)
  *   "box_quantile" the grid spans the [q, 1-q] percentile range of the level-0 means per axis (default 5e-4;
  *                 0 = full bounding box); outliers are clamped into border cells, results do not depend on it
  *   "rng_base"    counter of the first OUTPUT flag of the first step; default = n
@@ -201,10 +204,12 @@ int hem_step_pairs(hem_ctx* ctx, int step, uint32_t* parent_idx, int64_t* off,
 int hem_nccl_unique_id(uint8_t* id_out);
 
 /* Join a communicator of `world` ranks.  After this, hem_build_pyramid must be
- * called collectively with identical arguments (and identical input arrays) on
- * every rank; each rank runs the gate and moment kernels for the parents of its
- * slab, the accepted pairs and the merged rows are all-gathered per level, so
- * every rank ends with the complete pyramid, bit-identical to a 1-GPU run. */
+ * called collectively with identical arguments (identical input arrays, and the
+ * same kind of pointer — host or device — for each argument) on every rank;
+ * each rank runs the gate and moment kernels for the parents of its slab, the
+ * accepted pairs and the merged rows are all-gathered per level, so every rank
+ * ends with the complete pyramid, bit-identical to a 1-GPU run.  Host inputs are
+ * uploaded in 1/world slices per rank and all-gathered (option "shard_upload"). */
 int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world);
 
 /* Pure host arithmetic, no GPU needed: the slab of parents (positions in grid-cell order)
