@@ -125,3 +125,45 @@ def multiscale_registration(pc1_list, pc2_list, init_trans, voxel_values, iter_v
             current = r.transformation
             out.append(r)
     return out
+
+
+def register_gaussian_clouds(first, second, hem_params=None, voxel_values=(5.0, 2.5, 2.0, 1.0), iter_values=(50, 30, 20, 10),
+                             init_trans=None, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
+                             seed: int = 0, device: int = 0):
+    """BASELINE configs[4] as one headless call: what the GUI does with its "Mixture" tab (HEM pyramid of each cloud,
+    qt_gaussian_mixture.py:42-58) followed by its "Multiscale" tab (coarse-to-fine ICP over the two pyramids,
+    qt_multiscale_registrator.py:203-230), everything staying on the GPU in between.
+
+    ``first`` / ``second``: tuples ``(xyz, colors, opacity, cov6, sh)`` of numpy arrays or torch CUDA tensors.
+    ``len(voxel_values) == len(iter_values) == hem_params.cluster_level + 1`` as in the reference.
+    The two pyramids are independent, so they are built from two host threads on the two contexts' streams (the C ABI
+    drops the GIL): their launch-bound coarse levels overlap on the one GPU.
+    Returns ``(results, ctx_first, ctx_second)``; the caller closes the contexts (they hold the pyramids).
+    """
+    import threading
+    from .hem import HemParams
+    p = hem_params or HemParams()
+    if len(iter_values) != len(voxel_values):
+        raise ValueError("The number of iteration and voxel values provided do not match.")
+    if len(iter_values) != p.cluster_level + 1:
+        raise ValueError("The number of iterations and the mixture levels do not match.")
+    ctxs = (HemContext(device, seed), HemContext(device, seed))
+    errs = []
+
+    def build(ctx, cloud):
+        try:
+            ctx.build(*cloud, cluster_level=p.cluster_level, hem_reduction=p.hem_reduction, distance_delta=p.distance_delta,
+                      color_delta=p.color_delta, decay_rate=p.decay_rate)
+        except Exception as e:          # surfaced on the calling thread below
+            errs.append(e)
+    threads = [threading.Thread(target=build, args=(c, x)) for c, x in zip(ctxs, (first, second))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        for c in ctxs:
+            c.close()
+        raise errs[0]
+    results = ctxs[0].icp_multiscale(ctxs[1], list(voxel_values), list(iter_values), init_trans, relative_fitness, relative_rmse)
+    return results, ctxs[0], ctxs[1]

@@ -38,6 +38,22 @@ with HemContext(0, seed=13) as ca, HemContext(0, seed=13) as cb:
         ca.icp_multiscale(cb, corr, iters)
         pipe = time.perf_counter() - t0
     out["pipeline_ms_wall"] = pipe * 1e3
+    # the two pyramids are independent: built from two host threads (ctypes drops the GIL) on the two contexts'
+    # streams, their launch-bound small levels overlap on the one GPU
+    import threading
+    for rep in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=c.build, args=tuple(d), kwargs=dict(cluster_level=L)) for c, d in ((ca, da), (cb, db))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        both = time.perf_counter() - t0
+        ca.icp_multiscale(cb, corr, iters)
+        pipe2 = time.perf_counter() - t0
+    out["two_builds_concurrent_ms_wall"] = both * 1e3
+    out["pipeline_concurrent_ms_wall"] = pipe2 * 1e3
     for rep in range(3):
         t0 = time.perf_counter()
         res = ca.icp_multiscale(cb, corr, iters)

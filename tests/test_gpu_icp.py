@@ -179,3 +179,33 @@ def test_do_icp_registration_mirror(hemctx):
     assert cs.shape == (r.n_correspondences, 2) and np.array_equal(cs[:, 1], o["correspondence"][cs[:, 0]])
     with pytest.raises(NotImplementedError):
         reg.do_icp_registration(src, tgt, np.eye(4), reg.LocalRegistrationParams(registration_type=reg.LocalRegistrationType.ICP_Color), hemctx)
+
+
+def test_register_gaussian_clouds_pipeline_matches_stepwise():
+    """The one-call pipeline (two pyramids built concurrently + coarse-to-fine ICP) gives exactly what the steps give
+    one after the other, and recovers the rigid motion."""
+    from gaussiansplattingregistration_b200.hem import HemContext, HemParams
+    from gaussiansplattingregistration_b200 import registration as reg
+    a = synth(50000, seed=301, density=5000.0)
+    b, T_true = rigid_copy(a, seed=302, max_rot_deg=5.0, max_trans_frac=0.02)
+    spacing = (1.0 / 5000.0) ** (1.0 / 3.0)
+    corr = [15 * spacing, 7.5 * spacing, 6 * spacing, 3 * spacing]
+    iters = [50, 30, 20, 10]
+    hp = HemParams(cluster_level=3)
+    res, ca, cb = reg.register_gaussian_clouds(a.arrays(), b.arrays(), hp, corr, iters, seed=13)
+    try:
+        with HemContext(0, seed=13) as sa, HemContext(0, seed=13) as sb:
+            sa.build(*a.arrays(), cluster_level=3)
+            sb.build(*b.arrays(), cluster_level=3)
+            for l in range(4):
+                assert np.array_equal(sa.level(l)["xyz"], ca.level(l)["xyz"]) and np.array_equal(sb.level(l)["sh"], cb.level(l)["sh"])
+            want = sa.icp_multiscale(sb, corr, iters)
+        for g, w in zip(res, want):
+            assert np.array_equal(g.transformation, w.transformation) and g.fitness == w.fitness and g.iterations == w.iterations
+    finally:
+        ca.close()
+        cb.close()
+    T = res[-1].transformation
+    assert np.abs(T[:3, :3] - T_true[:3, :3]).max() < 2e-2 and np.abs(T[:3, 3] - T_true[:3, 3]).max() < 5e-2
+    with pytest.raises(ValueError, match="mixture levels do not match"):
+        reg.register_gaussian_clouds(a.arrays(), b.arrays(), hp, corr[:3], iters[:3])
