@@ -17,6 +17,17 @@ d = synth(6000, seed=7, density=200000.0)
 ctx2 = HemContext(0, 7)
 ctx2.build(*d.arrays(), cluster_level=2)
 print("dense sizes", [ctx2.level_size(l) for l in range(3)], ctx2.step_stats(0)["n_pairs"])
+# ICP consumer: two small pyramids, coarse-to-fine; plus host arrays with correspondences and a fringe (no match) part
+from gaussiansplattingregistration_b200.synth import rigid_copy
+a = synth(20000, seed=8, density=5000.0)
+b, T = rigid_copy(a, seed=9, max_rot_deg=5.0, max_trans_frac=0.02)
+ca, cb = HemContext(0, 3), HemContext(0, 3)
+ca.build(*a.arrays(), cluster_level=2); cb.build(*b.arrays(), cluster_level=2)
+r = ca.icp_multiscale(cb, [1.0, 0.5, 0.2], [20, 10, 5])
+print("icp sizes", [x.iterations for x in r], r[-1].fitness)
+src = np.concatenate([a.xyz.astype(np.float64), a.xyz.astype(np.float64)[:500] + 50.0])
+r2 = ca.icp(src, b.xyz.astype(np.float64), None, 0.3, max_iteration=6, with_correspondences=True)
+print("icp sizes", r2.iterations, r2.n_correspondences, int((r2.correspondence < 0).sum()))
 PY
 for tool in memcheck racecheck initcheck; do
   echo "#### $tool"
