@@ -50,7 +50,7 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_bit_identical_to_single(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -62,4 +62,4 @@ def test_multi_gpu_bit_identical_to_single(world):
     for r in range(world):
         ok, msg, sizes = ret[r]
         assert ok, msg
-    assert ret[0][2] == ret[1][2]
+    assert all(ret[r][2] == ret[0][2] for r in range(world))
