@@ -181,8 +181,9 @@ def run_reference_arm(a, rank, world):
     value = tot / secs
     sample = f"{n_s}-Gaussian sample of the workload (same density/params/levels), per-level createClusterLevel time"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-           "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1),
+           "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak" if world == 1 else "strong",       # same label as the GPU arm: one cloud, whatever N is
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": wall, "gpu_launches": 0}
