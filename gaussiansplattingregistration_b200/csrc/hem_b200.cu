@@ -767,7 +767,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->sh_pending) CKR(wait_sh(ctx));
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
-            pdl(k_moments, (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4), MOM_WARPS * 32, 0, st)(M);
+            const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
+            if (Fp <= 64) pdl(k_moments<2>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            else if (Fp <= 128) pdl(k_moments<4>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            else pdl(k_moments<8>, mgrid, MOM_WARPS * 32, 0, st)(M);
             CK(cudaGetLastError());
             ctx->n_launches++;
         }
@@ -1076,7 +1079,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
 {
     if (!ctx) return HEM_ERR_INVALID;
     ctx->err.clear();
-    if (n < 0 || sh_floats < 0 || sh_floats > 64) { ctx->err = "n must be >= 0 and 0 <= sh_floats <= 64"; return HEM_ERR_INVALID; }
+    if (n < 0 || sh_floats < 0 || sh_floats > 256) { ctx->err = "n must be >= 0 and 0 <= sh_floats <= 256"; return HEM_ERR_INVALID; }
     if (n > 0 && (!xyz || !color || !opacity || !cov6 || (sh_floats > 0 && !sh))) { ctx->err = "null input array"; return HEM_ERR_INVALID; }
     if (!(hem_reduction > 0)) { ctx->err = "hem_reduction must be > 0"; return HEM_ERR_INVALID; }
     if (cluster_level > 64) { ctx->err = "cluster_level > 64"; return HEM_ERR_INVALID; }

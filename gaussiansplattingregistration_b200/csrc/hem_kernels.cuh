@@ -920,6 +920,8 @@ struct MomArgs {
     unsigned long long* counters;
 };
 
+// NSH = SH accumulators per lane: rows of up to 32*NSH floats (2 covers SH degree <= 3, the 3DGS standard)
+template <int NSH>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
 k_moments(MomArgs A)
 {
@@ -956,7 +958,10 @@ k_moments(MomArgs A)
             const float x = __shfl_sync(full, pq0.x, 0), y = __shfl_sync(full, pq0.y, 0), z = __shfl_sync(full, pq0.z, 0);
             pmj = (j == 0) ? x : (j == 1 ? y : (j == 2 ? z : 0.0f));
         }
-        float accg = 0.0f, sh0 = 0.0f, sh1 = 0.0f;
+        float accg = 0.0f;
+        float shacc[NSH];
+#pragma unroll
+        for (int q = 0; q < NSH; ++q) shacc[q] = 0.0f;
 
         auto finalize = [&]() {
             // normalise, mixture.cpp:219-226
@@ -972,13 +977,16 @@ k_moments(MomArgs A)
             const size_t orow_i = A.by_rank ? (size_t)srank : (size_t)(tb + cur);
             if (lane < 16) ogeof[16 * orow_i + lane] = outv;
             float* orow = A.osh + orow_i * Fp;
-            if (lane < Fp) orow[lane] = fm(inv_w, sh0);
-            if (lane + 32 < Fp) orow[lane + 32] = fm(inv_w, sh1);
+#pragma unroll
+            for (int q = 0; q < NSH; ++q)
+                if (lane + 32 * q < Fp) orow[lane + 32 * q] = fm(inv_w, shacc[q]);
         };
         auto advance = [&]() {
             finalize();
             ++cur;
-            accg = 0.0f; sh0 = 0.0f; sh1 = 0.0f;
+            accg = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NSH; ++q) shacc[q] = 0.0f;
             if (cur < nb) {
                 nextb = __shfl_sync(full, off, cur + 1);
                 const float x = __shfl_sync(full, pq0.x, cur), y = __shfl_sync(full, pq0.y, cur), z = __shfl_sync(full, pq0.z, cur);
@@ -1001,7 +1009,7 @@ k_moments(MomArgs A)
             const int cnt = (int)min(32u, pb - k0);
             // phase 2: rows, 8 pairs in flight
             for (int g = 0; g < cnt; g += 8) {
-                float gv[8], v0[8], v1[8], wc[8];
+                float gv[8], vs[NSH][8], wc[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int c = min(g + u, cnt - 1);
@@ -1009,8 +1017,8 @@ k_moments(MomArgs A)
                     wc[u] = __shfl_sync(full, w, c);
                     gv[u] = geof[16 * (size_t)cc + j];
                     const float* row = A.sh + (size_t)cc * Fp;
-                    v0[u] = lane < Fp ? row[lane] : 0.0f;
-                    v1[u] = lane + 32 < Fp ? row[lane + 32] : 0.0f;
+#pragma unroll
+                    for (int q = 0; q < NSH; ++q) vs[q][u] = lane + 32 * q < Fp ? row[lane + 32 * q] : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -1022,8 +1030,8 @@ k_moments(MomArgs A)
                         // DESIGN.md §2): fused multiply-adds
                         const float val = (j == 3) ? 1.0f : (is_cov ? fmaf(da, db, gv[u]) : gv[u]);
                         accg = fmaf(wc[u], val, accg);
-                        sh0 = fmaf(v0[u], wc[u], sh0);
-                        sh1 = fmaf(v1[u], wc[u], sh1);
+#pragma unroll
+                        for (int q = 0; q < NSH; ++q) shacc[q] = fmaf(vs[q][u], wc[u], shacc[q]);
                     }
                 }
             }
@@ -1066,8 +1074,7 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
         if (lane < 4) ogeo[4 * dst + lane] = v;
         const float* srow = sh + (size_t)ci * Fp;
         float* drow = osh + dst * Fp;
-        if (lane < Fp) drow[lane] = srow[lane];
-        if (lane + 32 < Fp) drow[lane + 32] = srow[lane + 32];
+        for (int q = lane; q < Fp; q += 32) drow[q] = srow[q];
     }
 }
 

@@ -84,7 +84,8 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value);
  *   color    [n*3]  raw SH-DC colour
  *   opacity  [n]    raw opacity
  *   cov6     [n*6]  packed covariance 00,01,02,11,12,22 (src/utils/general_utils.py:20-29)
- *   sh       [n*sh_floats] SH rest coefficients (may be NULL iff sh_floats == 0)
+ *   sh       [n*sh_floats] SH rest coefficients (may be NULL iff sh_floats == 0); 0 <= sh_floats <= 256
+ *            (45 at SH degree 3; the reference's FeatureVector takes any length, featurevector.cpp:20-63)
  *   weight   [n] or NULL (=> 1.0f, mixture.cpp:315); non-NULL for teacher-forced per-level parity
  *   level0_parent_mask [n] or NULL (=> Philox flags with counters 0..n-1)
  * Arguments 9-13 are CreateMixture's clusterLevel, hemReduction, distanceDelta,

@@ -383,6 +383,30 @@ def test_gpu_extreme_parameters_vs_oracle(port, n, red, dd, cd, decay, deg):
                              params=dict(hem_reduction=red, distance_delta=dd, color_delta=cd, decay_rate=decay))
 
 
+@pytest.mark.parametrize("deg", [4, 5, 8])
+def test_gpu_wide_sh_rows_vs_oracle(port, deg):
+    """SH degrees above the 3DGS standard (72 / 105 / 240 rest floats per splat): the reference takes any
+    FeatureVector length (featurevector.cpp:20-63), so does the moment kernel (one instantiation per row width)."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(9000, seed=40 + deg, density=8000.0, sh_degree=deg)
+    assert c.sh.shape[1] == 3 * ((deg + 1) ** 2 - 1)
+    with HemContext(0, seed=9) as ctx:
+        ctx.set_option("keep_pairs", 1)
+        ctx.build(*c.arrays(), cluster_level=2)
+        r = port.run(*c.arrays(), levels=2, seed=9)
+
+        def children(l):
+            ch = r.children(l)
+            return ch["parent_idx"], ch["off"], ch["child"]
+        # device-resident input (SH rows used in place) gives the same bits as the host path
+        import torch
+        want = [ctx.level(l) for l in range(3)]
+        ctx.build(*[torch.from_numpy(x).cuda() for x in c.arrays()], cluster_level=2)
+        for l in range(3):
+            assert np.array_equal(ctx.level(l)["sh"], want[l]["sh"]) and np.array_equal(ctx.level(l)["xyz"], want[l]["xyz"])
+        compare_free_running(ctx, r.level, children, 2, f"sh degree {deg}", port_run=r)     # (re-builds teacher-forced steps)
+
+
 @pytest.mark.parametrize("case", ["offset", "duplicates", "planar", "tiny"])
 def test_gpu_awkward_geometry_vs_oracle(port, case):
     """Inputs that stress the grid: a cloud far from the origin (FP32 cell arithmetic), coincident
