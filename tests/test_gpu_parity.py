@@ -555,3 +555,50 @@ def test_gpu_plane_inlier_merging_matches_oracle(port):
             assert_level_close(got[d], want, what=f"plane merging level {d}")
         else:
             assert abs(got[d]["xyz"].shape[0] - want["xyz"].shape[0]) <= 4
+
+
+def test_gpu_random_sweep_vs_oracle(port):
+    """The sweep that pins the oracle to the compiled reference (tests/test_oracle.py), now CUDA vs oracle: 24 random
+    small clouds, random CreateMixture arguments / densities / SH degrees, a quarter of them with non-finite or
+    indefinite components.  First step: masks, child sets, counts, order and NaN pattern exact, values within 1e-4."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    rng = np.random.default_rng(2026)
+    for case in range(24):
+        n = int(rng.integers(50, 1500))
+        deg = int(rng.integers(0, 5))
+        c = synth(n, seed=1000 + case, density=float(rng.choice([500.0, 5000.0, 50000.0])), sh_degree=deg)
+        red = float(rng.choice([1.0, 1.5, 3.0, 8.0]))
+        dd = float(rng.choice([0.5, 2.0, 3.0, 6.0]))
+        cd = float(rng.choice([0.0, 1.0, 2.5, 10.0]))
+        decay = float(rng.choice([0.05, 1.0, 30.0]))
+        if case % 4 == 3:
+            k = rng.integers(0, n, size=5)
+            c.cov6[k[0]] = 0.0
+            c.cov6[k[1], 0] = -abs(c.cov6[k[1], 0])
+            c.cov6[k[2], 3] = np.nan
+            c.xyz[k[3], 1] = np.nan
+            c.opacity[k[4]] = np.inf
+        seed = 77 + case
+        what = f"case {case}: n={n} deg={deg} red={red} dd={dd} cd={cd} decay={decay}"
+        r = port.run(*c.arrays(), 1, red, dd, cd, decay, seed=seed)
+        mask = r.level(0)["is_parent"].astype(np.uint8)
+        g_ctx = HemContext(0, seed=seed)        # the seed is a property of the context
+        try:
+            g_ctx.set_option("keep_pairs", 1)
+            g_ctx.build(*c.arrays(), cluster_level=1, hem_reduction=red, distance_delta=dd, color_delta=cd,
+                        decay_rate=decay)
+            assert np.array_equal(g_ctx.level(0, True)["is_parent"].astype(np.uint8), mask), what
+            assert g_ctx.level_size(1) == r.size(1), what
+            gp, pc = g_ctx.step_pairs(0), r.children(0)
+            assert_children_equal(gp["parent_idx"], gp["off"], gp["child"], pc["parent_idx"], pc["off"], pc["child"], what=what)
+            a, b = g_ctx.level(1, True), r.level(1)
+            assert np.array_equal(a["is_parent"], b["is_parent"]), what
+            for key in ("xyz", "colors", "opacity", "cov6", "sh", "weight"):
+                fa, fb = np.isfinite(a[key]), np.isfinite(b[key])
+                assert np.array_equal(fa, fb), (what, key)
+                m = fa & fb
+                num = np.linalg.norm(a[key][m].astype(np.float64) - b[key][m])
+                den = max(np.linalg.norm(b[key][m].astype(np.float64)), 1e-30)
+                assert num / den < TOL, (what, key, num / den)
+        finally:
+            g_ctx.close()
