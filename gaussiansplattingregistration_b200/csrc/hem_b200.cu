@@ -71,7 +71,8 @@ struct hem_ctx {
     int prep_level = -1;
     int64_t prep_n = 0;
     Ctl prep_stats;
-    bool dense_hint = false;       // last step had more than 4 accepted pairs per component
+    bool dense_hint = false;       // last step had more than 4 accepted pairs per component (or its claim table overflowed)
+    int redo_depth = 0;            // guards the redo recursion of run_step
     size_t pool_min = 0;           // pair pool size learned from an overflow
     // robust grid box of the current build (percentile range of the level-0 means, see k_boxhist)
     bool box_valid = false;
@@ -672,7 +673,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->csr_child, std::max<int64_t>(P, 1) * 4));
         CKR(ensure(ctx, ctx->csr_wl, std::max<int64_t>(P, 1) * 4));
         // claim-table regime decided here so that the single-GPU chunk copy can file the claims in the same pass
-        const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n);
+        // (dense_hint is also what a failed claim summation leaves behind: a few children claimed by thousands of
+        // parents overflow the table even when P <= 4n — the redo must then take the sort path, not the table again)
+        const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n && !ctx->dense_hint);
         const bool fuse_claims = use_claims && G == 1 && P > 0;
         if (use_claims && P > 0) {
             CKR(ensure(ctx, ctx->claims, (size_t)n * CLAIM_K * 8));
@@ -827,7 +830,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             if (claims_failed) ctx->dense_hint = true;
             ctx->prep_valid = carried;
             ctx->prep_level = l; ctx->prep_n = n; ctx->prep_stats = ps;
-            return run_step(ctx, l, hem_reduction, distance_delta, color_delta, decay_rate, rng_base);
+            if (++ctx->redo_depth > 4) { ctx->redo_depth = 0; ctx->err = "clustering step did not settle after 4 redos (pool / claim table)"; return HEM_ERR_STATE; }
+            const int rc = run_step(ctx, l, hem_reduction, distance_delta, color_delta, decay_rate, rng_base);
+            ctx->redo_depth = 0;
+            return rc;
         }
         P = (int64_t)pairs;
         S.n_pairs = P;

@@ -602,3 +602,39 @@ def test_gpu_random_sweep_vs_oracle(port):
                 assert num / den < TOL, (what, key, num / den)
         finally:
             g_ctx.close()
+
+
+@pytest.mark.timeout(180)
+def test_gpu_hub_children_overflow_claim_table_with_few_pairs(port):
+    """A handful of children claimed by THOUSANDS of parents while the pair count stays below 4 per component
+    (what a degenerate needle-like Gaussian does in a heavy-tailed scene: NaN passes every gate,
+    mixture.cpp:122-133): the claim table overflows although the level is 'sparse', and the redo must go through
+    the sort path instead of trying the table again (this used to recurse forever)."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    n = 9000
+    c = synth(n, seed=77, density=5000.0, sh_degree=1)
+    rng = np.random.default_rng(5)
+    c.xyz[:] = rng.uniform(0.0, 0.02, (n, 3)).astype(np.float32)          # everything inside everybody's radius
+    c.colors[:] = (np.arange(n, dtype=np.float32) * 50.0)[:, None]        # colour gate: nobody accepts anybody ...
+    seed = 31
+    mask = port.run(*c.arrays(), levels=0, seed=seed).level(0)["is_parent"]
+    hubs = np.nonzero(~mask.astype(bool))[0][:5]
+    c.colors[hubs] = np.nan                                                # ... except the hubs: NaN passes
+    r = port.run(*c.arrays(), levels=1, seed=seed)
+    pc = r.children(0)
+    per_child = np.bincount(pc["child"], minlength=n)
+    assert per_child[hubs].min() > 1000 and len(pc["child"]) <= 4 * n       # the regime this test is about
+    with HemContext(0, seed=seed) as ctx:
+        ctx.build(*c.arrays(), cluster_level=1)                             # fast flow -> table overflow -> redo by sorting
+        assert ctx.level_size(1) == r.size(1)
+        a, b = ctx.level(1, True), r.level(1)
+        assert np.array_equal(a["is_parent"], b["is_parent"])
+        for key in ("xyz", "colors", "opacity", "cov6", "weight", "sh"):
+            fa, fb = np.isfinite(a[key]), np.isfinite(b[key])
+            assert np.array_equal(fa, fb), key
+            assert group_relerr(a[key][fa & fb], b[key][fa & fb]) < TOL, key
+        ctx.set_option("keep_pairs", 1)                                     # general flow, same answer and the pair lists
+        ctx.build(*c.arrays(), cluster_level=1)
+        gp = ctx.step_pairs(0)
+        assert_children_equal(gp["parent_idx"], gp["off"], gp["child"], pc["parent_idx"], pc["off"], pc["child"], what="hubs")
+        assert np.array_equal(ctx.level(1, True)["weight"], a["weight"])
