@@ -79,6 +79,8 @@ struct hem_ctx {
     float box_lo[3] = { 0, 0, 0 }, box_hi[3] = { 0, 0, 0 };
     double box_q = 5e-4;
     int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
+    uint32_t heavy_pairs = 16384;  // parents with more accepted pairs are accumulated by k_moments_heavy (0 = never)
+    bool heavy_hint = false;       // a previous step met such a parent: launch k_moments_heavy from now on
     double cell_scale = 0.55;
     double cell_occupancy = 1.3;   // lower bound of the cell edge in units of the mean component spacing
     bool rng_base_set = false;
@@ -97,7 +99,7 @@ struct hem_ctx {
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
     DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist;
+    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
@@ -427,11 +429,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
 
     // ---- S1 prep --------------------------------------------------------------------------
     // control block + the arrays that must start from zero live in one allocation: one memset per step
-    //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) | cnt_c (n) ]
+    //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) | cnt_c (n) | heavy-parent list ]
     const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1 + 64) * 4 + 255) / 256 * 256;   // +64: all-gather padding
     const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
     const size_t off_cntc = off_sumlw + ((size_t)n * 4 + 255) / 256 * 256;
-    const size_t ctl_bytes = (off_cntc + (size_t)n * 4 + 15) / 16 * 16;
+    const size_t off_heavy = off_cntc + ((size_t)n * 4 + 255) / 256 * 256;      // one byte per moment ticket
+    const size_t ctl_bytes = (off_heavy + (size_t)(n / MOM_B + 2) + 15) / 16 * 16;
     CKR(ensure(ctx, ctx->ctlbuf, ctl_bytes));
     Ctl* d_ctl = ctx->ctlbuf.as<Ctl>();
     unsigned long long* d_counters = d_ctl->counters;
@@ -439,6 +442,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     uint32_t* d_pair_cnt = (uint32_t*)((char*)ctx->ctlbuf.p + off_cnt);
     float* d_sumlw = (float*)((char*)ctx->ctlbuf.p + off_sumlw);
     uint32_t* d_cnt_c = (uint32_t*)((char*)ctx->ctlbuf.p + off_cntc);
+    uint8_t* d_heavy = (uint8_t*)ctx->ctlbuf.p + off_heavy;
     const int set = l & 1;
     DevBuf& RAD = set ? ctx->radius2 : ctx->radius;
     DevBuf& SAFE = set ? ctx->psafe2 : ctx->psafe;
@@ -493,6 +497,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     int64_t P = 0;
     size_t pool_cap_used = 0, chunk_cap_final = 0;
     const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
+    bool launched_heavy = false;
     if (have_pairs) {
         // ---- S2 grid --------------------------------------------------------------------------
         GridP g;
@@ -760,6 +765,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
         M.counters = d_counters;
         M.pool_cap = fast ? (unsigned long long)pool_cap : ~0ull;
+        M.hv_flag = d_heavy;
+        M.hv_done = nullptr;
+        M.n_heavy = &d_ctl->n_heavy;
+        M.heavy_thr = ctx->heavy_pairs;
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
@@ -774,6 +783,26 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             if (Fp <= 64) pdl(k_moments<2>, mgrid, MOM_WARPS * 32, 0, st)(M);
             else if (Fp <= 128) pdl(k_moments<4>, mgrid, MOM_WARPS * 32, 0, st)(M);
             else pdl(k_moments<8>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            // Parents above heavy_pairs pairs are split over the whole grid (k_moments_heavy).  An ordinary cloud has
+            // none, so the kernel is launched only once such a parent has been seen (the step that meets the first one
+            // is redone, like a pool overflow); sharded runs launch it always so that the ranks never disagree.
+            launched_heavy = ctx->heavy_pairs && (ctx->heavy_hint || G > 1);
+            if (launched_heavy) {
+                const int nsh = Fp <= 64 ? 2 : (Fp <= 128 ? 4 : 8);
+                const size_t items = (size_t)std::max<int64_t>(P, (int64_t)pool_cap) / HEAVY_CHUNK + (size_t)np + 8;
+                CKR(ensure(ctx, ctx->heavy_part, items * (size_t)(16 + 32 * nsh) * 4));
+                if (ctx->heavy_done.cap < (size_t)np * 4) {        // per-parent item counters: zero once, the kernel re-zeroes what it used
+                    CKR(ensure(ctx, ctx->heavy_done, (size_t)np * 4));
+                    CK(cudaMemsetAsync(ctx->heavy_done.p, 0, ctx->heavy_done.cap, st));
+                }
+                M.hv_done = ctx->heavy_done.as<uint32_t>();
+                const unsigned hgrid = (unsigned)ctx->sm_count * 2;
+                if (nsh == 2) pdl(k_moments_heavy<2>, hgrid, MOM_WARPS * 32, 0, st)(M, ctx->heavy_part.as<float>());
+                else if (nsh == 4) pdl(k_moments_heavy<4>, hgrid, MOM_WARPS * 32, 0, st)(M, ctx->heavy_part.as<float>());
+                else pdl(k_moments_heavy<8>, hgrid, MOM_WARPS * 32, 0, st)(M, ctx->heavy_part.as<float>());
+                CK(cudaGetLastError());
+                ctx->n_launches++;
+            }
             CK(cudaGetLastError());
             ctx->n_launches++;
         }
@@ -823,7 +852,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const unsigned long long pairs = packed & ((1ull << POOL_BITS) - 1ull), nch = packed >> POOL_BITS;
         const bool overflow = pairs > pool_cap_used || nch > chunk_cap_final;
         const bool claims_failed = ctx->h_counters[C_FAIL] != 0;
-        if (overflow || claims_failed) {
+        const bool heavy_missed = !overflow && ctx->heavy_pairs && !launched_heavy && ctx->h_ctl->n_heavy > 0;
+        if (heavy_missed) ctx->heavy_hint = true;
+        if (overflow || claims_failed || heavy_missed) {
             // nothing was corrupted (pool writes are guarded, the claim summation bailed out): redo the step
             // with a larger pool / through the sort path; the carried prep of THIS level is still intact
             if (overflow) ctx->pool_min = (size_t)pairs + (size_t)pairs / 4 + 1024;
@@ -1037,7 +1068,7 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done,
                       &ctx->icp_src, &ctx->icp_tgt, &ctx->icp_box, &ctx->icp_key, &ctx->icp_key2, &ctx->icp_val, &ctx->icp_val2,
                       &ctx->icp_rows, &ctx->icp_start, &ctx->icp_part, &ctx->icp_state, &ctx->icp_corr };
     for (DevBuf* b : all) release(*b);
@@ -1071,6 +1102,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "shard_upload") ctx->shard_upload = value != 0;
+    else if (k == "heavy_pairs") { if (!(value >= 0) || value > 4e9) { ctx->err = "heavy_pairs out of range"; return HEM_ERR_INVALID; } ctx->heavy_pairs = (uint32_t)value; }
     else if (k == "cell_occupancy") { if (!(value >= 0)) { ctx->err = "cell_occupancy must be >= 0"; return HEM_ERR_INVALID; } ctx->cell_occupancy = value; }
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }
     else if (k == "rng_base") { ctx->rng_base_set = value >= 0; ctx->rng_base = (uint64_t)value; }

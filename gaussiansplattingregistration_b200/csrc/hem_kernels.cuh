@@ -66,6 +66,8 @@ struct Ctl {
     unsigned int n_radius;          // parents with finite positive radius
     unsigned int n_parents;
     unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
+    unsigned int n_heavy;           // moment tickets deferred to k_moments_heavy in this step
+    unsigned int pad_heavy;
     unsigned long long sum_radius_fx;   // sum of (log2(radius) + 128) in 2^-16 units over the parents with a finite positive
                                         // radius: the grid cell is sized from the GEOMETRIC mean radius (robust against the
                                         // heavy tail of splat scales); integer adds are order-independent, so the cell size —
@@ -918,7 +920,13 @@ struct MomArgs {
     unsigned long long pool_cap;  // the kernel does nothing if the pair pool overflowed (the host redoes the step)
     float4* ogeo; float* osh;
     unsigned long long* counters;
+    // heavy parents (see k_moments_heavy): tickets holding a parent with more than heavy_thr pairs are not
+    // accumulated here but flagged in hv_flag[ticket] (and counted in *n_heavy, control block) for k_moments_heavy;
+    // which tickets are deferred depends on the pair counts only, never on scheduling
+    uint8_t* hv_flag; uint32_t* hv_done; unsigned int* n_heavy; uint32_t heavy_thr;
 };
+
+constexpr uint32_t HEAVY_CHUNK = 2048;    // pairs per work item of the heavy kernel
 
 // NSH = SH accumulators per lane: rows of up to 32*NSH floats (2 covers SH degree <= 3, the 3DGS standard)
 template <int NSH>
@@ -946,6 +954,19 @@ k_moments(MomArgs A)
         if (tb >= A.t_end) break;
         const int nb = min(MOM_B, A.t_end - tb);
         const uint32_t off = (lane <= nb) ? A.pair_off_s[tb + lane] : 0xffffffffu;
+        if (A.heavy_thr) {
+            // one parent is one warp here; a parent with 10^5 pairs (a degenerate giant whose gates all pass) would
+            // be the whole step's critical path: its ticket goes to k_moments_heavy, which splits it over the grid
+            const uint32_t nxt = __shfl_down_sync(full, off, 1);
+            const bool hv = lane < nb && (nxt - off) > A.heavy_thr;
+            if (__ballot_sync(full, hv)) {
+                if (lane == 0) {
+                    A.hv_flag[(tb - A.t_begin) / MOM_B] = 1;
+                    atomicAdd(A.n_heavy, 1u);
+                }
+                continue;
+            }
+        }
         const uint2 pt = (lane < nb) ? A.ptab[tb + lane] : make_uint2(0u, 0u);
         float4 pq0 = make_float4(0, 0, 0, 0);
         if (lane < nb) pq0 = A.geo[4 * (size_t)pt.x];               // parent means (outer-product origin)
@@ -1039,6 +1060,129 @@ k_moments(MomArgs A)
         while (cur < nb - 1) advance();      // trailing parents without pairs
         finalize();
         __syncwarp();
+    }
+}
+
+// Heavy parents.  Every deferred ticket's parents are cut into work items of HEAVY_CHUNK pairs that the whole grid
+// shares; each item leaves an un-normalised partial row, and the warp that finishes a parent's last item adds the
+// partial rows in item order and finalises the row exactly like k_moments does.  Item boundaries and the combine
+// order depend only on the pair count, so the result is deterministic.
+template <int NSH>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+k_moments_heavy(MomArgs A, float* __restrict__ part)
+{
+    pdl_enter();
+    if (pool_overflowed(A.counters, A.pool_cap)) return;
+    if (*A.n_heavy == 0) return;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = gridDim.x * MOM_WARPS;
+    const int Fp = A.Fp;
+    const float* geof = reinterpret_cast<const float*>(A.geo);
+    float* ogeof = reinterpret_cast<float*>(A.ogeo);
+    const int j = lane & 15;
+    const bool is_cov = j >= 4 && j <= 9;
+    const int sa = (j <= 6) ? 0 : (j <= 8 ? 1 : 2);
+    const int sb = (j == 4) ? 0 : ((j == 5 || j == 7) ? 1 : 2);
+    constexpr int PR = 16 + 32 * NSH;            // floats per partial row
+    const int ntick = (A.t_end - A.t_begin + MOM_B - 1) / MOM_B;
+    for (int tbase = 0; tbase < ntick; tbase += 32) {
+      unsigned fm_ = __ballot_sync(full, tbase + lane < ntick && A.hv_flag[tbase + lane] != 0);
+      while (fm_) {
+        const int tb = A.t_begin + (tbase + __ffs(fm_) - 1) * MOM_B;
+        fm_ &= fm_ - 1;
+        const int nb = min(MOM_B, A.t_end - tb);
+        for (int q = 0; q < nb; ++q) {
+            const int t = tb + q;
+            const uint32_t pa = A.pair_off_s[t], pb = A.pair_off_s[t + 1];
+            const uint32_t nch = max(1u, (pb - pa + HEAVY_CHUNK - 1) / HEAVY_CHUNK);
+            const uint2 pt = A.ptab[t];
+            const float4 pq0 = A.geo[4 * (size_t)pt.x];
+            const float pmj = (j == 0) ? pq0.x : (j == 1 ? pq0.y : (j == 2 ? pq0.z : 0.0f));
+            for (uint32_t c = gwarp; c < nch; c += nwarps) {
+                const uint32_t s0 = pa + c * HEAVY_CHUNK, s1 = min(pb, s0 + HEAVY_CHUNK);
+                float accg = 0.0f;
+                float shacc[NSH];
+#pragma unroll
+                for (int x = 0; x < NSH; ++x) shacc[x] = 0.0f;
+                for (uint32_t k0 = s0; k0 < s1; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    uint32_t ch = 0;
+                    float w = 0.0f;
+                    if (k < s1) {
+                        const uint2 pr = A.csr_s[k];
+                        ch = pr.x;
+                        w = fm(fd(__uint_as_float(pr.y), A.sumlw[ch]), geof[16 * (size_t)ch + 3]);
+                    }
+                    const int cnt = (int)min(32u, s1 - k0);
+                    for (int g = 0; g < cnt; g += 8) {
+                        float gv[8], vs[NSH][8], wc[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int cc_i = min(g + u, cnt - 1);
+                            const uint32_t cc = __shfl_sync(full, ch, cc_i);
+                            wc[u] = __shfl_sync(full, w, cc_i);
+                            gv[u] = geof[16 * (size_t)cc + j];
+                            const float* row = A.sh + (size_t)cc * Fp;
+#pragma unroll
+                            for (int x = 0; x < NSH; ++x) vs[x][u] = lane + 32 * x < Fp ? row[lane + 32 * x] : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (g + u < cnt) {
+                                const float dv = fs(gv[u], pmj);
+                                const float da = __shfl_sync(full, dv, sa), db = __shfl_sync(full, dv, sb);
+                                const float val = (j == 3) ? 1.0f : (is_cov ? fmaf(da, db, gv[u]) : gv[u]);
+                                accg = fmaf(wc[u], val, accg);
+#pragma unroll
+                                for (int x = 0; x < NSH; ++x) shacc[x] = fmaf(vs[x][u], wc[u], shacc[x]);
+                            }
+                        }
+                    }
+                }
+                // partial rows of consecutive parents never collide: item index = pa / CHUNK + c + t
+                const size_t ibase = (size_t)(pa / HEAVY_CHUNK) + (size_t)t;
+                float* pr = part + (ibase + c) * PR;
+                if (lane < 16) __stcg(pr + lane, accg);
+#pragma unroll
+                for (int x = 0; x < NSH; ++x) __stcg(pr + 16 + 32 * x + lane, shacc[x]);
+                __threadfence();
+                uint32_t prev = 0;
+                if (lane == 0) prev = atomicAdd(&A.hv_done[t], 1u);
+                prev = __shfl_sync(full, prev, 0);
+                if (prev == nch - 1) {
+                    // last item of this parent: add the partial rows in item order, then finalise (mixture.cpp:219-226)
+                    __threadfence();
+                    float sg = 0.0f;
+                    float ss[NSH];
+#pragma unroll
+                    for (int x = 0; x < NSH; ++x) ss[x] = 0.0f;
+                    for (uint32_t cc = 0; cc < nch; ++cc) {
+                        const float* r = part + (ibase + cc) * PR;
+                        sg += __ldcg(r + j);
+#pragma unroll
+                        for (int x = 0; x < NSH; ++x) ss[x] += __ldcg(r + 16 + 32 * x + lane);
+                    }
+                    const float w_s = __shfl_sync(full, sg, 3);
+                    const float inv_w = fd(1.0f, w_s);
+                    const float scaled = fm(inv_w, sg);
+                    const float dm = fs(scaled, pmj);
+                    const float da = __shfl_sync(full, dm, sa), db = __shfl_sync(full, dm, sb);
+                    float outv = is_cov ? fs(scaled, fm(da, db)) : scaled;
+                    if (j == 3) outv = w_s;
+                    if (j == 11 || j == 15) outv = 0.0f;
+                    const size_t orow_i = A.by_rank ? (size_t)pt.y : (size_t)t;
+                    if (lane < 16) ogeof[16 * orow_i + lane] = outv;
+                    float* orow = A.osh + orow_i * Fp;
+#pragma unroll
+                    for (int x = 0; x < NSH; ++x)
+                        if (lane + 32 * x < Fp) orow[lane + 32 * x] = fm(inv_w, ss[x]);
+                    if (lane == 0) A.hv_done[t] = 0u;         // ready for the next step
+                }
+                __syncwarp();
+            }
+        }
+      }
     }
 }
 
