@@ -780,13 +780,20 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
         if (my_np > 0) {
             const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
-            if (Fp <= 64) pdl(k_moments<2>, mgrid, MOM_WARPS * 32, 0, st)(M);
-            else if (Fp <= 128) pdl(k_moments<4>, mgrid, MOM_WARPS * 32, 0, st)(M);
-            else pdl(k_moments<8>, mgrid, MOM_WARPS * 32, 0, st)(M);
             // Parents above heavy_pairs pairs are split over the whole grid (k_moments_heavy).  An ordinary cloud has
-            // none, so the kernel is launched only once such a parent has been seen (the step that meets the first one
-            // is redone, like a pool overflow); sharded runs launch it always so that the ranks never disagree.
+            // none, so the deferring variant and the heavy kernel run only once such a parent has been reported (the
+            // step that meets the first one is redone, like a pool overflow); sharded runs use them always so that
+            // the ranks never disagree.
             launched_heavy = ctx->heavy_pairs && (ctx->heavy_hint || G > 1);
+            if (launched_heavy) {
+                if (Fp <= 64) pdl(k_moments<2, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else if (Fp <= 128) pdl(k_moments<4, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else pdl(k_moments<8, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            } else {
+                if (Fp <= 64) pdl(k_moments<2, false>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else if (Fp <= 128) pdl(k_moments<4, false>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else pdl(k_moments<8, false>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            }
             if (launched_heavy) {
                 const int nsh = Fp <= 64 ? 2 : (Fp <= 128 ? 4 : 8);
                 const size_t items = (size_t)std::max<int64_t>(P, (int64_t)pool_cap) / HEAVY_CHUNK + (size_t)np + 8;

@@ -929,7 +929,9 @@ struct MomArgs {
 constexpr uint32_t HEAVY_CHUNK = 2048;    // pairs per work item of the heavy kernel
 
 // NSH = SH accumulators per lane: rows of up to 32*NSH floats (2 covers SH degree <= 3, the 3DGS standard)
-template <int NSH>
+// DEFER = false: the ordinary kernel; it only reports that a heavy parent exists (the host then redoes the step
+// with DEFER = true, which leaves the tickets of heavy parents to k_moments_heavy).
+template <int NSH, bool DEFER>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
 k_moments(MomArgs A)
 {
@@ -959,12 +961,16 @@ k_moments(MomArgs A)
             // be the whole step's critical path: its ticket goes to k_moments_heavy, which splits it over the grid
             const uint32_t nxt = __shfl_down_sync(full, off, 1);
             const bool hv = lane < nb && (nxt - off) > A.heavy_thr;
-            if (__ballot_sync(full, hv)) {
-                if (lane == 0) {
-                    A.hv_flag[(tb - A.t_begin) / MOM_B] = 1;
-                    atomicAdd(A.n_heavy, 1u);
+            if (DEFER) {
+                if (__ballot_sync(full, hv)) {
+                    if (lane == 0) {
+                        A.hv_flag[(tb - A.t_begin) / MOM_B] = 1;
+                        atomicAdd(A.n_heavy, 1u);
+                    }
+                    continue;
                 }
-                continue;
+            } else if (hv) {
+                atomicAdd(A.n_heavy, 1u);       // rare; tells the host to redo the step with the heavy path
             }
         }
         const uint2 pt = (lane < nb) ? A.ptab[tb + lane] : make_uint2(0u, 0u);
