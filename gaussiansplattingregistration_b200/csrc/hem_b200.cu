@@ -768,7 +768,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         M.hv_flag = d_heavy;
         M.hv_done = nullptr;
         M.n_heavy = &d_ctl->n_heavy;
-        M.heavy_thr = ctx->heavy_pairs;
+        M.heavy_thr = (G == 1) ? ctx->heavy_pairs : 0u;
         if (G == 1) {
             M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
         } else {
@@ -782,9 +782,9 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
             // Parents above heavy_pairs pairs are split over the whole grid (k_moments_heavy).  An ordinary cloud has
             // none, so the deferring variant and the heavy kernel run only once such a parent has been reported (the
-            // step that meets the first one is redone, like a pool overflow); sharded runs use them always so that
-            // the ranks never disagree.
-            launched_heavy = ctx->heavy_pairs && (ctx->heavy_hint || G > 1);
+            // step that meets the first one is redone, like a pool overflow).  Sharded runs keep the ordinary kernel:
+            // a redo decided by one rank alone would take the ranks out of step (not validated on several GPUs yet).
+            launched_heavy = ctx->heavy_pairs && ctx->heavy_hint && G == 1;
             if (launched_heavy) {
                 if (Fp <= 64) pdl(k_moments<2, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
                 else if (Fp <= 128) pdl(k_moments<4, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
@@ -859,7 +859,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const unsigned long long pairs = packed & ((1ull << POOL_BITS) - 1ull), nch = packed >> POOL_BITS;
         const bool overflow = pairs > pool_cap_used || nch > chunk_cap_final;
         const bool claims_failed = ctx->h_counters[C_FAIL] != 0;
-        const bool heavy_missed = !overflow && ctx->heavy_pairs && !launched_heavy && ctx->h_ctl->n_heavy > 0;
+        const bool heavy_missed = !overflow && ctx->world == 1 && ctx->heavy_pairs && !launched_heavy && ctx->h_ctl->n_heavy > 0;
         if (heavy_missed) ctx->heavy_hint = true;
         if (overflow || claims_failed || heavy_missed) {
             // nothing was corrupted (pool writes are guarded, the claim summation bailed out): redo the step

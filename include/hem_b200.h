@@ -67,6 +67,8 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
  *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own
  *                 PCIe link and the slices are all-gathered over NVLink; 0 -> every rank uploads everything
+ *   "heavy_pairs" parents with more accepted pairs than this are accumulated by the grid-wide split kernel
+ *                 instead of one warp (default 16384; 0 = never; single GPU)
  *   "cell_occupancy" lower bound of the grid cell edge in units of the mean component spacing (default 1.3; 0 = off)
  *   "box_quantile" the grid spans the [q, 1-q] percentile range of the level-0 means per axis (default 5e-4;
  *                 0 = full bounding box); outliers are clamped into border cells, results do not depend on it
