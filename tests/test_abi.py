@@ -97,3 +97,37 @@ def test_synth_is_deterministic():
     det = (-c[:, 2] * c[:, 2] * c[:, 3] + 2 * c[:, 1] * c[:, 2] * c[:, 4] - c[:, 0] * c[:, 4] * c[:, 4]
            - c[:, 1] * c[:, 1] * c[:, 5] + c[:, 0] * c[:, 3] * c[:, 5])
     assert (det > 0).all()
+
+
+def test_registration_host_side_types():
+    """Host-only pieces of the ICP mirror: result unpacking, Open3D-style correspondence_set, point extraction,
+    parameter defaults equal to the reference's (src/params/registration_parameters.py:8-15)."""
+    import numpy as np
+    from gaussiansplattingregistration_b200 import _capi
+    from gaussiansplattingregistration_b200 import registration as reg
+    from gaussiansplattingregistration_b200.hem import IcpResult
+    flat = np.zeros(_capi.ICP_RESULT_LEN)
+    flat[:16] = np.eye(4).ravel()
+    flat[16:24] = [0.75, 0.01, 7, 3, 1, 0.5, 1000, 0.1]
+    corr = np.array([2, -1, 0, 5], np.int32)
+    r = IcpResult.from_flat(flat, corr)
+    assert r.fitness == 0.75 and r.inlier_rmse == 0.01 and r.iterations == 7 and r.n_correspondences == 3
+    assert r.stop_reason == 1 and r.grid_cells == 1000 and np.array_equal(r.transformation, np.eye(4))
+    assert np.array_equal(r.correspondence_set, np.array([[0, 2], [2, 0], [3, 5]], np.int32))
+    with pytest.raises(ValueError):
+        IcpResult.from_flat(flat, None).correspondence_set
+
+    class PC:
+        points = [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]]
+    for src in (PC(), {"points": PC.points}, PC.points, np.asarray(PC.points, np.float32)):
+        p = reg._points_of(src)
+        assert p.dtype == np.float64 and p.shape == (2, 3) and p.flags["C_CONTIGUOUS"]
+    d = reg.LocalRegistrationParams()
+    assert (d.max_correspondence, d.relative_fitness, d.relative_rmse, d.max_iteration, d.k_value) == (5.0, 1e-6, 1e-6, 30, 0.0)
+    assert d.rejection_type is reg.KernelLossFunctionType.Loss_None
+    assert [t.instance_name for t in reg.LocalRegistrationType] == ["Point-to-Point ICP", "Point-to-Plane ICP", "Colored ICP",
+                                                                    "Generalized ICP"]
+    with pytest.raises(NotImplementedError):      # raised before any GPU work
+        reg.do_icp_registration(PC(), PC(), np.eye(4), reg.LocalRegistrationParams(registration_type=reg.LocalRegistrationType.ICP_General))
+    with pytest.raises(ValueError, match="mixture levels do not match"):
+        reg.register_gaussian_clouds((), (), None, [1.0], [5])
