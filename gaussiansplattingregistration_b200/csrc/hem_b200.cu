@@ -44,6 +44,8 @@ struct Level {
 
 struct StepStats {
     int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0, n_certified = 0;
+    int64_t n_parents_local = 0, n_pairs_local = 0;   // this rank's share of the gate / moment work (multi-GPU)
+    int shards = 1;                                   // ranks the step was sharded over
     double cell_size = 0, max_radius = 0;
     double ms_host = 0;       // host time spent enqueueing the step (up to its closing sync)
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
@@ -582,6 +584,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         std::vector<int64_t> tb(G + 1);
         for (int q = 0; q <= G; ++q) tb[q] = slab_bound(np, q, G);
         const int64_t my_np = tb[R + 1] - tb[R];
+        S.n_parents_local = my_np; S.shards = G;
         CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->ptab, np * 8));
@@ -653,6 +656,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             if (attempt == 7) { ctx->err = "pair pool overflow persisted"; return HEM_ERR_STATE; }
         }
         pool_cap_used = pool_cap; chunk_cap_final = chunk_cap_used;
+        if (!fast) S.n_pairs_local = (int64_t)ctx->h_counters[C_POOL];
         std::vector<int64_t> pb(G + 1, 0);          // pair offsets at the slab bounds
         if (fast) {
             pb[1] = (int64_t)pool_cap;              // capacity; the true count is read on the device / at the final sync
@@ -873,8 +877,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             ctx->redo_depth = 0;
             return rc;
         }
-        P = (int64_t)pairs;
-        S.n_pairs = P;
+        if (S.shards == 1) {        // sharded steps: P is the global count from the exchange, `pairs` is this rank's share
+            P = (int64_t)pairs;
+            S.n_pairs = P;
+        }
+        S.n_pairs_local = (int64_t)pairs;
     }
     ctx->dense_hint = P > 4 * n;
     const int64_t norph = (int64_t)ctx->h_counters[C_NORPH];
@@ -1140,6 +1147,8 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
 
     ctx->prep_valid = false;
     ctx->box_valid = false;
+    ctx->sh_pending = false;       // a build that failed half-way must not leave a stale wait / all-gather behind
+    ctx->sh_gather_chunk = 0;
     // level 0 = the input (Mixture::initMixture, mixture.cpp:287-333)
     Level& L0 = ctx->levels[0];
     L0.n = n;
@@ -1325,6 +1334,7 @@ int hem_step_stats(const hem_ctx* ctx, int step, double* out)
     for (int i = 0; i < 9; ++i) out[9 + i] = S.ms[i];
     out[18] = (double)S.n_certified;
     out[19] = S.ms_host;
+    out[20] = (double)S.n_parents_local; out[21] = (double)S.n_pairs_local; out[22] = (double)S.shards;
     return HEM_OK;
 }
 
@@ -1372,6 +1382,7 @@ int hem_comm_init(hem_ctx* ctx, const uint8_t* id, int rank, int world)
 {
     if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return HEM_ERR_INVALID;
     if (world == 1) { ctx->rank = 0; ctx->world = 1; return HEM_OK; }
+    if (world > 64) { ctx->err = "more than 64 ranks are not supported (in-place exchange padding)"; return HEM_ERR_INVALID; }
     if (!nccl_load()) { ctx->err = g_nccl.err; return HEM_ERR_NCCL; }
     CK(cudaSetDevice(ctx->device));
     NcclId nid;

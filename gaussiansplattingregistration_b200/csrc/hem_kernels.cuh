@@ -906,8 +906,15 @@ __global__ void k_segsum(const uint32_t* __restrict__ key, const float* __restri
 //                            in list order; lane j owns element j of the geometry row
 //   parent boundary        : normalise, det, flag, validity, one 64-byte + one SH row store
 // ---------------------------------------------------------------------------
+#ifndef HEM_MOM_U
+#define HEM_MOM_U 8
+#endif
+#ifndef HEM_MOM_MINB
+#define HEM_MOM_MINB 1
+#endif
 constexpr int MOM_WARPS = 8;
 constexpr int MOM_B = HEM_MOM_B;
+constexpr int MOM_U = HEM_MOM_U;          // child rows in flight per warp
 
 struct MomArgs {
     const float4* geo; const float* sh; int Fp;
@@ -932,7 +939,7 @@ constexpr uint32_t HEAVY_CHUNK = 2048;    // pairs per work item of the heavy ke
 // DEFER = false: the ordinary kernel; it only reports that a heavy parent exists (the host then redoes the step
 // with DEFER = true, which leaves the tickets of heavy parents to k_moments_heavy).
 template <int NSH, bool DEFER>
-__global__ void __launch_bounds__(MOM_WARPS * 32)
+__global__ void __launch_bounds__(MOM_WARPS * 32, HEM_MOM_MINB)
 k_moments(MomArgs A)
 {
     pdl_enter();
@@ -1035,10 +1042,10 @@ k_moments(MomArgs A)
             }
             const int cnt = (int)min(32u, pb - k0);
             // phase 2: rows, 8 pairs in flight
-            for (int g = 0; g < cnt; g += 8) {
-                float gv[8], vs[NSH][8], wc[8];
+            for (int g = 0; g < cnt; g += MOM_U) {
+                float gv[MOM_U], vs[NSH][MOM_U], wc[MOM_U];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < MOM_U; ++u) {
                     const int c = min(g + u, cnt - 1);
                     const uint32_t cc = __shfl_sync(full, ch, c);
                     wc[u] = __shfl_sync(full, w, c);
@@ -1048,7 +1055,7 @@ k_moments(MomArgs A)
                     for (int q = 0; q < NSH; ++q) vs[q][u] = lane + 32 * q < Fp ? row[lane + 32 * q] : 0.0f;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < MOM_U; ++u) {
                     if (g + u < cnt) {                                  // uniform
                         while (k0 + g + u == nextb && cur < nb - 1) advance();   // parent boundary (empty parents too)
                         const float dv = fs(gv[u], pmj);

@@ -15,7 +15,8 @@ import numpy as np
 from . import _capi
 
 STAT_NAMES = ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out", "grid_cells", "cell_size",
-              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments", "n_certified_parents", "ms_host_enqueue")
+              "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments", "n_certified_parents", "ms_host_enqueue",
+              "n_parents_local", "n_pairs_local", "shards")
 
 
 @dataclass
@@ -61,11 +62,20 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
-def _ptr(x):
-    """(pointer, keepalive) of a numpy array or torch tensor, None passes through."""
+def _ptr(x, device=None, dtype="torch.float32"):
+    """(pointer, keepalive) of a numpy array or torch tensor, None passes through.  A torch CUDA tensor is used in
+    place through its data pointer, so it must already have the element type the C ABI reads and live on the
+    context's GPU: anything else would be reinterpreted silently."""
     if x is None:
         return None, None
     if _is_torch(x):
+        if x.is_cuda:
+            if device is not None and x.device.index != device:
+                raise ValueError(f"tensor is on cuda:{x.device.index}, the context runs on cuda:{device}")
+            if dtype is not None and str(x.dtype) != dtype:
+                raise TypeError(f"expected a {dtype} tensor, got {x.dtype}")
+        elif dtype is not None and str(x.dtype) != dtype:
+            x = x.to(getattr(__import__("torch"), dtype.split(".")[1]))
         if not x.is_contiguous():
             x = x.contiguous()
         return C.c_void_p(x.data_ptr()), x
@@ -119,6 +129,8 @@ class HemContext:
         self.device = device
         self.sh_floats = 0
         self.rank, self.world = 0, 1
+        self._user_stream = False          # set_stream() was called: the caller owns the ordering
+        self._borrowed = None              # device inputs the library aliases beyond the call (level-0 SH rows)
 
     # -- plumbing -----------------------------------------------------------
     def _check(self, code: int):
@@ -147,7 +159,22 @@ class HemContext:
         self._check(self._lib.hem_set_option(self._h, name.encode(), float(value)))
 
     def set_stream(self, stream_handle: int | None):
+        self._user_stream = stream_handle is not None
         self._check(self._lib.hem_set_stream(self._h, C.c_void_p(stream_handle or 0)))
+
+    def _follow_torch_stream(self, *arrays):
+        """Device tensors are produced and consumed asynchronously on torch's current stream: unless the caller
+        chose a stream, run on that one so the library's reads and writes are ordered with the caller's kernels."""
+        if self._user_stream:
+            return
+        if any(a is not None and _is_torch(a) and a.is_cuda for a in arrays):
+            self._check(self._lib.hem_set_stream(self._h, C.c_void_p(self._torch_stream())))
+
+    def _torch_stream(self) -> int:
+        """Handle of torch's current stream on the context's GPU; the legacy default stream (handle 0 in torch) is
+        passed as cudaStreamLegacy, because 0 means "the context's own stream" to hem_set_stream."""
+        import torch
+        return torch.cuda.current_stream(self.device).cuda_stream or 1
 
     # -- multi-GPU ------------------------------------------------------------------
     def init_distributed(self, rank: int | None = None, world: int | None = None, unique_id: bytes | None = None):
@@ -174,14 +201,18 @@ class HemContext:
             sh = None if F == 0 else np.ascontiguousarray(sh, dtype=np.float32)
             weight = None if weight is None else np.ascontiguousarray(weight, dtype=np.float32)
             parent_mask = None if parent_mask is None else np.ascontiguousarray(parent_mask, dtype=np.uint8)
+        self._follow_torch_stream(xyz, colors, opacity, cov6, sh, weight, parent_mask)
         keep = []
         ptrs = []
         for a in (xyz, colors, opacity, cov6, sh if F else None, weight):
-            p, k = _ptr(a)
+            p, k = _ptr(a, self.device)
             ptrs.append(p)
             keep.append(k)
-        pm, k = _ptr(parent_mask)
+        pm, k = _ptr(parent_mask, self.device, "torch.uint8")
         keep.append(k)
+        # a device-resident SH array is used in place as level 0 (no copy): it has to outlive the call for
+        # level(0) / level_torch(0) to stay valid, so the context holds on to it until the next build
+        self._borrowed = keep[4] if F and _is_torch(keep[4]) and keep[4].is_cuda else None
         self.sh_floats = F
         self._check(self._lib.hem_build_pyramid(self._h, *ptrs, n, F, int(cluster_level), float(hem_reduction),
                                                 float(distance_delta), float(color_delta), float(decay_rate), pm))
@@ -208,11 +239,9 @@ class HemContext:
         the registration_icp call of the reference's do_icp_registration,
         src/utils/local_registration_util.py:76-100).  source/target: [n,3] float64 numpy arrays or
         torch CUDA tensors."""
-        ps, ks = _ptr(source if _is_torch(source) else np.asarray(source, np.float64))
-        pt, kt = _ptr(target if _is_torch(target) else np.asarray(target, np.float64))
-        for a in (ks, kt):
-            if _is_torch(a):
-                assert str(a.dtype) == "torch.float64", "ICP points must be float64"
+        self._follow_torch_stream(source, target)
+        ps, ks = _ptr(source if _is_torch(source) else np.asarray(source, np.float64), self.device, "torch.float64")
+        pt, kt = _ptr(target if _is_torch(target) else np.asarray(target, np.float64), self.device, "torch.float64")
         ns, nt = int(ks.shape[0]), int(kt.shape[0])
         res = np.zeros(_capi.ICP_RESULT_LEN, np.float64)
         T0 = None if init is None else np.ascontiguousarray(np.asarray(init, np.float64).reshape(4, 4))
@@ -316,6 +345,8 @@ class HemContext:
         import torch
         n, F = self.level_size(level), self.sh_floats
         dev = torch.device("cuda", self.device)
+        if not self._user_stream:       # the new tensors belong to torch's current stream: write them on it
+            self._check(self._lib.hem_set_stream(self._h, C.c_void_p(self._torch_stream())))
         out = dict(xyz=torch.empty((n, 3), dtype=torch.float32, device=dev),
                    colors=torch.empty((n, 3), dtype=torch.float32, device=dev),
                    opacity=torch.empty(n, dtype=torch.float32, device=dev),
@@ -336,7 +367,7 @@ class HemContext:
         buf = (C.c_double * _capi.STEP_STATS_LEN)()
         self._check(self._lib.hem_step_stats(self._h, step, buf))
         d = dict(zip(STAT_NAMES, list(buf)))
-        for k in STAT_NAMES[:7]:
+        for k in STAT_NAMES[:7] + STAT_NAMES[18:19] + STAT_NAMES[20:23]:
             d[k] = int(d[k])
         return d
 

@@ -179,9 +179,11 @@ int hem_clear_outputs(hem_ctx* ctx);
  *   16 ms_k_gate (the gate kernel alone)  17 ms_k_moments (the moment kernel alone)
  *   18 n_certified_parents (parents whose covariance is certified for the smd pre-test)
  *   19 ms_host_enqueue (host wall time spent enqueueing the step, up to its closing sync)
+ *   20 n_parents_local  21 n_pairs_local (this rank's share of the gate / moment work in a multi-GPU build;
+ *      equal to 1 and 2 on one GPU)  22 shards (ranks the step was sharded over; 1 = built whole on every rank)
  * ms_* are CUDA-event times on the context's stream and are 0 unless the
  * "timing" option is set. */
-#define HEM_STEP_STATS_LEN 20
+#define HEM_STEP_STATS_LEN 23
 int hem_step_stats(const hem_ctx* ctx, int step, double* out);
 
 /* Cumulative counters of the context: "launches" (kernels of this library
