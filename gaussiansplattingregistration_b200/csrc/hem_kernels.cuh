@@ -67,7 +67,7 @@ struct Ctl {
     unsigned int n_parents;
     unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
     unsigned int n_heavy;           // moment tickets deferred to k_moments_heavy in this step
-    unsigned int pad_heavy;
+    unsigned int n_heavy_gate;      // parents whose search box has more rows of cells than the gate's row threshold
     unsigned long long sum_radius_fx;   // sum of (log2(radius) + 128) in 2^-16 units over the parents with a finite positive
                                         // radius: the grid cell is sized from the GEOMETRIC mean radius (robust against the
                                         // heavy tail of splat scales); integer adds are order-independent, so the cell size —
@@ -449,9 +449,23 @@ struct GateArgs {
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
     uint32_t* pair_cnt;          // [np+1] same, indexed by canonical rank (single GPU; NULL when sharded)
     uint2* pool; unsigned long long pool_cap;
-    uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count, prefix inside the parent)
+    uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count | segment tag << 8, prefix inside the parent / segment)
     unsigned long long* counters;
+    // heavy parents (DRAFT, not validated on a GPU yet): a parent whose search box has more than row_defer (y,z) rows of
+    // cells is not scanned by one warp; k_gate<true> cuts its rows into segments of GATE_SEG_ROWS that the grid shares.
+    int row_report;              // > 0: count parents above this many rows in *n_heavy_gate (tells the host to redo)
+    int row_defer;               // > 0: leave such parents to k_gate<true> (flag in hvg_flag[t])
+    uint8_t* hvg_flag;           // [np]
+    unsigned int* n_heavy_gate;  // control block
+    uint32_t* seg_cnt;           // [segments] accepted pairs of a segment
+    uint32_t* seg_off;           // [segments] exclusive prefix inside its parent (written by the parent's last segment)
+    uint32_t* seg_done;          // [np] finished segments of a parent (self-resetting)
+    const uint32_t* hv_parent;   // [n_hv] heavy parents in cell order            } written by k_gate_heavy_index
+    const uint32_t* hv_segbase;  // [n_hv + 1] first global segment of each       }
+    uint32_t* hv_hdr;            // [0] number of heavy parents, [1] number of segments, [2] ticket counter
 };
+
+constexpr int GATE_SEG_ROWS = 256;           // rows of cells per work item of the heavy gate
 
 // conservative cell box of a parent's search sphere along one axis (DESIGN.md "grid range")
 __device__ __forceinline__ void cell_range(float q, float rr, float o, float inv_h, int g, int& lo, int& hi)
@@ -494,6 +508,9 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
                        __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
 }
 
+// HEAVY = false: the ordinary kernel (one warp per parent, tickets of A.tb parents).
+// HEAVY = true : only the parents flagged in hvg_flag; one ticket = one segment of GATE_SEG_ROWS rows of one parent.
+template <bool HEAVY>
 __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
 k_gate(GateArgs A)
 {
@@ -514,11 +531,32 @@ k_gate(GateArgs A)
     for (;;) {
         // one ticket = A.tb (<= GATE_TB) consecutive parents: three same-address atomics per parent (ticket,
         // pool, chunk) serialised at the L2 and were 13 % of the kernel's stall samples
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
-        const int tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * A.tb;
-        if (tfirst >= A.t_end) break;
-        const int tlast = min(tfirst + A.tb, A.t_end);
+        int tfirst, tlast;
+        uint32_t seg_id = 0, seg_local = 0, seg_first = 0, seg_n = 0;     // HEAVY only
+        if (!HEAVY) {
+            unsigned long long ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
+            tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * A.tb;
+            if (tfirst >= A.t_end) break;
+            tlast = min(tfirst + A.tb, A.t_end);
+        } else {
+            // one ticket = one segment of rows of one heavy parent; the parent is found by bisecting the segment bases
+            uint32_t it = 0;
+            if (lane == 0) it = atomicAdd(&A.hv_hdr[2], 1u);
+            it = __shfl_sync(full, it, 0);
+            if (it >= A.hv_hdr[1]) break;
+            uint32_t lo = 0, hi = A.hv_hdr[0];                    // hv_segbase[lo] <= it < hv_segbase[hi]
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (A.hv_segbase[mid] <= it) lo = mid; else hi = mid;
+            }
+            tfirst = (int)A.hv_parent[lo];
+            tlast = tfirst + 1;
+            seg_id = it;
+            seg_first = A.hv_segbase[lo];
+            seg_n = A.hv_segbase[lo + 1] - seg_first;
+            seg_local = it - seg_first;
+        }
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
@@ -560,7 +598,7 @@ k_gate(GateArgs A)
                     if (room) A.pool[base + k] = make_uint2(__float_as_uint(c0.w) & 0x7fffffffu, __float_as_uint(wl));
                 }
                 if (lane == 0 && cid < A.chunk_cap)
-                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on, total_out);
+                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on | (HEAVY ? (seg_id + 1u) << 8 : 0u), total_out);
                 total_out += (uint32_t)on;
                 on = 0;
                 __syncwarp();
@@ -635,13 +673,22 @@ k_gate(GateArgs A)
             const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
+            if (!HEAVY) {
+                if (A.row_report > 0 && nrows > A.row_report && lane == 0) atomicAdd(A.n_heavy_gate, 1u);
+                if (A.row_defer > 0 && nrows > A.row_defer) {          // uniform: left to k_gate<true>
+                    if (lane == 0) A.hvg_flag[t] = 1;
+                    continue;
+                }
+            }
+            const int rb_begin = HEAVY ? (int)seg_local * GATE_SEG_ROWS : 0;
+            const int rb_end = HEAVY ? min(nrows, rb_begin + GATE_SEG_ROWS) : nrows;
 
-            for (int rb = 0; rb < nrows; rb += 32) {
+            for (int rb = rb_begin; rb < rb_end; rb += 32) {
                 // one (y,z) row of cells per lane: cull rows the sphere misses, trim the x range of
                 // the others to the chord, fetch the [begin,end) run of slots, then scan the lengths
                 uint32_t ra = 0, len = 0;
                 const int rrow = rb + lane;
-                if (rrow < nrows) {
+                if (rrow < rb_end) {
                     const int y = y0 + rrow % ny, z = z0 + rrow / ny;
                     float lo = A.g.oy + (float)y * hc, hi = lo + hc;
                     float pad = (fabsf(A.g.oy) + fabsf(hi) + hc) * 4e-6f;
@@ -721,12 +768,90 @@ k_gate(GateArgs A)
             if (q2n > 0) stage_b(q2n);
             flush();
         }
-        if (lane == 0) {
-            A.pair_cnt_s[t] = total_out;
-            if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
+        if (!HEAVY) {
+            if (lane == 0) {
+                A.pair_cnt_s[t] = total_out;
+                if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
+            }
+        } else {
+            // the segment's count; the warp that finishes the parent's last segment turns the counts into offsets
+            // (segment order = row order, so the parent's CSR order does not depend on scheduling)
+            uint32_t prev = 0;
+            if (lane == 0) {
+                A.seg_cnt[seg_id] = total_out;
+                __threadfence();
+                prev = atomicAdd(&A.seg_done[t], 1u);
+            }
+            prev = __shfl_sync(full, prev, 0);
+            if (prev == seg_n - 1) {
+                __threadfence();
+                uint32_t run = 0;
+                for (uint32_t b = 0; b < seg_n; b += 32) {
+                    const uint32_t k = b + lane;
+                    const uint32_t c = k < seg_n ? __ldcg(&A.seg_cnt[seg_first + k]) : 0u;
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(full, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (k < seg_n) A.seg_off[seg_first + k] = run + incl - c;
+                    run += __shfl_sync(full, incl, 31);
+                }
+                if (lane == 0) {
+                    A.pair_cnt_s[t] = run;
+                    if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = run;
+                    A.seg_done[t] = 0u;
+                }
+            }
         }
         __syncwarp();
       }
+    }
+}
+
+// DRAFT (heavy gate): compact list of the parents flagged by k_gate<false>, in cell order, with the first global
+// segment of each.  One block; runs only in steps that use the heavy path.
+__global__ void __launch_bounds__(256)
+k_gate_heavy_index(const uint8_t* __restrict__ hvg_flag, const float4* __restrict__ pinfo, int t_begin, int t_end,
+                   uint32_t cap, uint32_t seg_cap, uint32_t* __restrict__ hv_parent, uint32_t* __restrict__ hv_segbase,
+                   uint32_t* __restrict__ hv_hdr)
+{
+    pdl_enter();
+    __shared__ uint32_t s_cnt[256], s_seg[256];
+    __shared__ uint32_t s_nhv, s_nseg, s_ovf;
+    if (threadIdx.x == 0) { s_nhv = 0; s_nseg = 0; s_ovf = 0; }
+    __syncthreads();
+    for (int base = t_begin; base < t_end; base += 256) {
+        const int t = base + (int)threadIdx.x;
+        uint32_t f = 0, ns = 0;
+        if (t < t_end && hvg_flag[t]) {
+            const float4 p6 = pinfo[(size_t)t * PINFO_F4 + 6];
+            const int ny = (int)(__float_as_uint(p6.z) >> 16) - (int)(__float_as_uint(p6.z) & 0xffffu) + 1;
+            const int nz = (int)(__float_as_uint(p6.w) >> 16) - (int)(__float_as_uint(p6.w) & 0xffffu) + 1;
+            f = 1;
+            ns = (uint32_t)((ny * nz + GATE_SEG_ROWS - 1) / GATE_SEG_ROWS);
+        }
+        s_cnt[threadIdx.x] = f;
+        s_seg[threadIdx.x] = ns;
+        __syncthreads();
+        if (threadIdx.x == 0) {                       // serial within the tile: heavy parents are rare
+            uint32_t nhv = s_nhv, nseg = s_nseg;
+            for (int k = 0; k < 256; ++k)
+                if (s_cnt[k]) {
+                    if (nhv < cap && nseg + s_seg[k] <= seg_cap) { hv_parent[nhv] = (uint32_t)(base + k); hv_segbase[nhv] = nseg; nseg += s_seg[k]; ++nhv; }
+                    else s_ovf = 1u;      // a deferred parent that does not fit: the host redoes the step without deferral
+                }
+            s_nhv = nhv; s_nseg = nseg;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        hv_segbase[s_nhv] = s_nseg;
+        hv_hdr[0] = s_nhv;
+        hv_hdr[1] = s_nseg;
+        hv_hdr[2] = 0u;
+        hv_hdr[3] = s_ovf;
     }
 }
 
@@ -739,7 +864,7 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long lon
                              unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
                              const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s,
                              const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c, uint2* __restrict__ claims,
-                             uint4* __restrict__ ovf, unsigned long long ovf_cap)
+                             uint4* __restrict__ ovf, unsigned long long ovf_cap, const uint32_t* __restrict__ seg_off)
 {
     pdl_enter();
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
@@ -748,7 +873,10 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long lon
     // launched over the chunk capacity; the number of chunks written is read on the device
     const unsigned long long nchunks = min(counters[C_POOL] >> POOL_BITS, chunk_cap);
     if (c >= nchunks) return;
-    const uint4 ch = chunks[c];
+    uint4 ch = chunks[c];
+    // a chunk of a heavy parent's segment carries the segment (index + 1) above the count: its prefix is relative to the segment
+    if (ch.z >> 8) ch.w += seg_off[(ch.z >> 8) - 1u];
+    ch.z &= 0xffu;
     const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
     const uint32_t srank = claims ? ptab[ch.x].y : 0u;
     for (uint32_t k = lane; k < ch.z; k += 32) {
