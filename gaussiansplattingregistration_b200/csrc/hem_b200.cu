@@ -83,6 +83,12 @@ struct hem_ctx {
     int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
     uint32_t heavy_pairs = 16384;  // parents with more accepted pairs are accumulated by k_moments_heavy (0 = never)
     bool heavy_hint = false;       // a previous step met such a parent: launch k_moments_heavy from now on
+    // the same for the gate, by rows of cells of the search box: a parent whose box has more rows than
+    // max(heavy_rows, heavy_rows_rel x the box of a parent of geometric-mean radius) is scanned by the grid in
+    // segments of GATE_SEG_ROWS rows instead of by one warp (heavy_rows = 0: never)
+    int heavy_rows = 128;
+    double heavy_rows_rel = 16.0;
+    bool heavy_gate_hint = false;
     double cell_scale = 0.55;
     double cell_occupancy = 1.3;   // lower bound of the cell edge in units of the mean component spacing
     bool rng_base_set = false;
@@ -101,7 +107,7 @@ struct hem_ctx {
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
     DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done;
+    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done, seg_info, hv_hdr, seg_cnt, seg_off, seg_done;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
@@ -187,6 +193,7 @@ int to_device(hem_ctx* ctx, const void* src, size_t bytes, DevBuf& stage, const 
     return HEM_OK;
 }
 
+constexpr uint32_t HEAVY_SEG_CAP = 1u << 20;    // row segments of heavy gate parents per step
 int g_gate_tb = 0;    // HEM_GATE_TICKET in the environment forces the gate ticket size (A/B measurements)
 bool g_pdl = true;   // HEM_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)
 
@@ -499,7 +506,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     int64_t P = 0;
     size_t pool_cap_used = 0, chunk_cap_final = 0;
     const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
-    bool launched_heavy = false;
+    bool launched_heavy = false, launched_gate_heavy = false;
     if (have_pairs) {
         // ---- S2 grid --------------------------------------------------------------------------
         GridP g;
@@ -625,6 +632,35 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;
             A.chunks = ctx->chunks.as<uint4>(); A.chunk_cap = chunk_cap;
             A.counters = d_counters;
+            // heavy parents of the gate (single GPU): reported always, deferred once the hint is set
+            constexpr uint32_t SEG_CAP = HEAVY_SEG_CAP;
+            int row_thr = 0;
+            if (ctx->heavy_rows > 0) {
+                const double gm = ps.n_radius ? std::exp2((double)ps.sum_radius_fx / 65536.0 / (double)ps.n_radius - 128.0) : S.cell_size;
+                const double side = 2.0 * gm / S.cell_size + 1.0;
+                row_thr = (int)std::min(1e9, std::max((double)ctx->heavy_rows, ctx->heavy_rows_rel * side * side));
+            }
+            launched_gate_heavy = row_thr > 0 && ctx->heavy_gate_hint && G == 1 && my_np > 0;
+            A.row_report = (G == 1) ? row_thr : 0;
+            A.row_defer = launched_gate_heavy ? row_thr : 0;
+            A.n_heavy_gate = &d_ctl->n_heavy_gate;
+            A.seg_cnt = nullptr; A.seg_off = nullptr; A.seg_done = nullptr;
+            A.seg_info = nullptr; A.seg_cap = SEG_CAP; A.hv_hdr = nullptr;
+            if (launched_gate_heavy) {
+                CKR(ensure(ctx, ctx->seg_info, (size_t)SEG_CAP * 16));
+                CKR(ensure(ctx, ctx->hv_hdr, 16));
+                CK(cudaMemsetAsync(ctx->hv_hdr.p, 0, 16, st));
+                CKR(ensure(ctx, ctx->seg_cnt, (size_t)SEG_CAP * 4));
+                CKR(ensure(ctx, ctx->seg_off, (size_t)SEG_CAP * 4));
+                if (ctx->seg_done.cap < (size_t)np * 4) {
+                    CKR(ensure(ctx, ctx->seg_done, (size_t)np * 4));
+                    CK(cudaMemsetAsync(ctx->seg_done.p, 0, ctx->seg_done.cap, st));
+                }
+                A.seg_cnt = ctx->seg_cnt.as<uint32_t>();
+                A.seg_off = ctx->seg_off.as<uint32_t>(); A.seg_done = ctx->seg_done.as<uint32_t>();
+                A.seg_info = ctx->seg_info.as<uint4>();
+                A.hv_hdr = ctx->hv_hdr.as<uint32_t>();
+            }
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
             if (my_np > 0) {
                 // ticket size: GATE_TB parents amortise the ticket/pool atomics on big levels; on small levels
@@ -633,7 +669,12 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 const int64_t resident_warps = (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS * GATE_WARPS;
                 A.tb = (int)std::max<int64_t>(1, std::min<int64_t>(GATE_TB, my_np / (2 * resident_warps)));
                 if (g_gate_tb > 0) A.tb = std::min(g_gate_tb, GATE_TB);
-                pdl(k_gate, (unsigned)std::min<int64_t>(blocks_for((my_np + A.tb - 1) / A.tb, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st)(A);
+                pdl(k_gate<false>, (unsigned)std::min<int64_t>(blocks_for((my_np + A.tb - 1) / A.tb, GATE_WARPS), (int64_t)ctx->sm_count * HEM_GATE_MINBLOCKS), GATE_WARPS * 32, 0, st)(A);
+                if (launched_gate_heavy) {
+                    // the flagged parents, cut into segments of rows, shared by the whole grid
+                    k_gate<true><<<(unsigned)ctx->sm_count * HEM_GATE_MINBLOCKS, GATE_WARPS * 32, 0, st>>>(A);
+                    ctx->n_launches += 1;
+                }
                 CK(cudaGetLastError());
                 ctx->n_launches++;
             }
@@ -693,10 +734,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (G == 1) {
             if (fast || nchunks > 0) {
                 const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
-                pdl(k_chunk_copy, blocks_for((int64_t)launch_chunks * 32, 256), 256, 0, st)(
+                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for((int64_t)launch_chunks * 32, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), ctx->ptab.as<uint2>(), d_cnt_c,
-                    fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P);
+                    fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P,
+                    launched_gate_heavy ? ctx->seg_off.as<uint32_t>() : nullptr);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
         } else {
@@ -706,10 +748,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             for (int q = 0; q < G; ++q) M = std::max(M, pb[q + 1] - pb[q]);
             CKR(ensure(ctx, ctx->csr_pad, (size_t)std::max<int64_t>(M, 1) * G * 8));
             if (nchunks > 0) {
-                pdl(k_chunk_copy, blocks_for((int64_t)nchunks * 32, 256), 256, 0, st)(
+                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for((int64_t)nchunks * 32, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>(),
-                    nullptr, nullptr, nullptr, nullptr, 0ull);
+                    nullptr, nullptr, nullptr, nullptr, 0ull, nullptr);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             CKR(allgather_equal(ctx, ctx->csr_pad.p, 8, M));
@@ -865,7 +907,23 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const bool claims_failed = ctx->h_counters[C_FAIL] != 0;
         const bool heavy_missed = !overflow && ctx->world == 1 && ctx->heavy_pairs && !launched_heavy && ctx->h_ctl->n_heavy > 0;
         if (heavy_missed) ctx->heavy_hint = true;
-        if (overflow || claims_failed || heavy_missed) {
+        if (launched_gate_heavy) {
+            // more deferred parents / segments than the index holds: give the heavy gate up for this context
+            if (ctx->h_counters[C_CHUNK] > (unsigned long long)HEAVY_SEG_CAP) {      // segments listed (published by k_gate<true>)
+                ctx->heavy_rows = 0;
+                ctx->heavy_gate_hint = false;
+                ctx->prep_valid = carried;
+                ctx->prep_level = l; ctx->prep_n = n; ctx->prep_stats = ps;
+                if (++ctx->redo_depth > 4) { ctx->redo_depth = 0; ctx->err = "clustering step did not settle after 4 redos"; return HEM_ERR_STATE; }
+                const int rc = run_step(ctx, l, hem_reduction, distance_delta, color_delta, decay_rate, rng_base);
+                ctx->redo_depth = 0;
+                return rc;
+            }
+        }
+        const bool gate_heavy_missed = !overflow && ctx->world == 1 && ctx->heavy_rows > 0 && !launched_gate_heavy &&
+                                       !ctx->heavy_gate_hint && ctx->h_ctl->n_heavy_gate > 0;
+        if (gate_heavy_missed) ctx->heavy_gate_hint = true;
+        if (overflow || claims_failed || heavy_missed || gate_heavy_missed) {
             // nothing was corrupted (pool writes are guarded, the claim summation bailed out): redo the step
             // with a larger pool / through the sort path; the carried prep of THIS level is still intact
             if (overflow) ctx->pool_min = (size_t)pairs + (size_t)pairs / 4 + 1024;
@@ -1082,7 +1140,8 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done, &ctx->seg_info, &ctx->hv_hdr,
+                      &ctx->seg_cnt, &ctx->seg_off, &ctx->seg_done,
                       &ctx->icp_src, &ctx->icp_tgt, &ctx->icp_box, &ctx->icp_key, &ctx->icp_key2, &ctx->icp_val, &ctx->icp_val2,
                       &ctx->icp_rows, &ctx->icp_start, &ctx->icp_part, &ctx->icp_state, &ctx->icp_corr };
     for (DevBuf* b : all) release(*b);
@@ -1116,6 +1175,8 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "shard_upload") ctx->shard_upload = value != 0;
+    else if (k == "heavy_rows_rel") { if (!(value >= 0)) { ctx->err = "heavy_rows_rel must be >= 0"; return HEM_ERR_INVALID; } ctx->heavy_rows_rel = value; }
+    else if (k == "heavy_rows") { if (!(value >= 0) || value > 1e9) { ctx->err = "heavy_rows out of range"; return HEM_ERR_INVALID; } ctx->heavy_rows = (int)value; }
     else if (k == "heavy_pairs") { if (!(value >= 0) || value > 4e9) { ctx->err = "heavy_pairs out of range"; return HEM_ERR_INVALID; } ctx->heavy_pairs = (uint32_t)value; }
     else if (k == "cell_occupancy") { if (!(value >= 0)) { ctx->err = "cell_occupancy must be >= 0"; return HEM_ERR_INVALID; } ctx->cell_occupancy = value; }
     else if (k == "cell_scale") { if (!(value > 0)) { ctx->err = "cell_scale must be > 0"; return HEM_ERR_INVALID; } ctx->cell_scale = value; }

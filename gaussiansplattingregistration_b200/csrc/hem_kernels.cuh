@@ -67,7 +67,7 @@ struct Ctl {
     unsigned int n_parents;
     unsigned int n_certified;       // parents whose covariance is certified for the smd pre-test
     unsigned int n_heavy;           // moment tickets deferred to k_moments_heavy in this step
-    unsigned int pad_heavy;
+    unsigned int n_heavy_gate;      // parents whose search box has more rows of cells than the gate's row threshold
     unsigned long long sum_radius_fx;   // sum of (log2(radius) + 128) in 2^-16 units over the parents with a finite positive
                                         // radius: the grid cell is sized from the GEOMETRIC mean radius (robust against the
                                         // heavy tail of splat scales); integer adds are order-independent, so the cell size —
@@ -449,9 +449,22 @@ struct GateArgs {
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
     uint32_t* pair_cnt;          // [np+1] same, indexed by canonical rank (single GPU; NULL when sharded)
     uint2* pool; unsigned long long pool_cap;
-    uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count, prefix inside the parent)
+    uint4* chunks; unsigned long long chunk_cap;   // (t, pool offset, count | segment tag << 8, prefix inside the parent / segment)
     unsigned long long* counters;
+    // heavy parents: a parent whose search box has more than row_defer (y,z) rows of cells is not scanned by one warp;
+    // k_gate<false> lists it as segments of GATE_SEG_ROWS rows (seg_info) and k_gate<true> shares the segments over the grid.
+    int row_report;              // > 0: count parents above this many rows in *n_heavy_gate (tells the host to redo)
+    int row_defer;               // > 0: leave such parents to k_gate<true>
+    unsigned int* n_heavy_gate;  // control block
+    uint32_t* seg_cnt;           // [segments] accepted pairs of a segment
+    uint32_t* seg_off;           // [segments] exclusive prefix inside its parent (written by the parent's last segment)
+    uint32_t* seg_done;          // [np] finished segments of a parent (self-resetting)
+    uint4* seg_info;             // [seg_cap] (t, segment inside the parent, segments of the parent, its first global segment)
+    uint32_t seg_cap;
+    uint32_t* hv_hdr;            // [1] segments listed (may exceed seg_cap: overflow), [2] ticket counter of k_gate<true>
 };
+
+constexpr int GATE_SEG_ROWS = 64;            // rows of cells per work item of the heavy gate
 
 // conservative cell box of a parent's search sphere along one axis (DESIGN.md "grid range")
 __device__ __forceinline__ void cell_range(float q, float rr, float o, float inv_h, int g, int& lo, int& hi)
@@ -494,6 +507,9 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
                        __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
 }
 
+// HEAVY = false: the ordinary kernel (one warp per parent, tickets of A.tb parents).
+// HEAVY = true : only the parents listed in seg_info; one ticket = one segment of GATE_SEG_ROWS rows of one parent.
+template <bool HEAVY>
 __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
 k_gate(GateArgs A)
 {
@@ -514,11 +530,29 @@ k_gate(GateArgs A)
     for (;;) {
         // one ticket = A.tb (<= GATE_TB) consecutive parents: three same-address atomics per parent (ticket,
         // pool, chunk) serialised at the L2 and were 13 % of the kernel's stall samples
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
-        const int tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * A.tb;
-        if (tfirst >= A.t_end) break;
-        const int tlast = min(tfirst + A.tb, A.t_end);
+        int tfirst, tlast;
+        uint32_t seg_id = 0, seg_local = 0, seg_first = 0, seg_n = 0;     // HEAVY only
+        if (!HEAVY) {
+            unsigned long long ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&A.counters[C_WORK], 1ull);
+            tfirst = A.t_begin + (int)__shfl_sync(full, ticket, 0) * A.tb;
+            if (tfirst >= A.t_end) break;
+            tlast = min(tfirst + A.tb, A.t_end);
+        } else {
+            // one ticket = one segment of rows of one heavy parent; the parent is found by bisecting the segment bases
+            uint32_t it = 0;
+            if (lane == 0) it = atomicAdd(&A.hv_hdr[2], 1u);
+            it = __shfl_sync(full, it, 0);
+            if (it == 0u && lane == 0) A.counters[C_CHUNK] = A.hv_hdr[1];      // segments listed: the host checks it against seg_cap
+            if (it >= min(A.hv_hdr[1], A.seg_cap)) break;
+            const uint4 si = A.seg_info[it];
+            tfirst = (int)si.x;
+            tlast = tfirst + 1;
+            seg_id = it;
+            seg_local = si.y;
+            seg_n = si.z;
+            seg_first = si.w;
+        }
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
@@ -560,7 +594,7 @@ k_gate(GateArgs A)
                     if (room) A.pool[base + k] = make_uint2(__float_as_uint(c0.w) & 0x7fffffffu, __float_as_uint(wl));
                 }
                 if (lane == 0 && cid < A.chunk_cap)
-                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on, total_out);
+                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on | (HEAVY ? (seg_id + 1u) << 8 : 0u), total_out);
                 total_out += (uint32_t)on;
                 on = 0;
                 __syncwarp();
@@ -635,13 +669,29 @@ k_gate(GateArgs A)
             const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
+            if (!HEAVY) {
+                if (A.row_report > 0 && nrows > A.row_report && lane == 0) atomicAdd(A.n_heavy_gate, 1u);
+                if (A.row_defer > 0 && nrows > A.row_defer) {          // uniform: left to k_gate<true>
+                    // the parent's segments take consecutive ids; which ids depends on scheduling, the results do not
+                    // (a segment's place in the parent's CSR range follows from its index inside the parent)
+                    const uint32_t ns = (uint32_t)((nrows + GATE_SEG_ROWS - 1) / GATE_SEG_ROWS);
+                    uint32_t sb = 0;
+                    if (lane == 0) sb = atomicAdd(&A.hv_hdr[1], ns);
+                    sb = __shfl_sync(full, sb, 0);
+                    if (sb + ns <= A.seg_cap)
+                        for (uint32_t k = lane; k < ns; k += 32) A.seg_info[sb + k] = make_uint4((uint32_t)t, k, ns, sb);
+                    continue;
+                }
+            }
+            const int rb_begin = HEAVY ? (int)seg_local * GATE_SEG_ROWS : 0;
+            const int rb_end = HEAVY ? min(nrows, rb_begin + GATE_SEG_ROWS) : nrows;
 
-            for (int rb = 0; rb < nrows; rb += 32) {
+            for (int rb = rb_begin; rb < rb_end; rb += 32) {
                 // one (y,z) row of cells per lane: cull rows the sphere misses, trim the x range of
                 // the others to the chord, fetch the [begin,end) run of slots, then scan the lengths
                 uint32_t ra = 0, len = 0;
                 const int rrow = rb + lane;
-                if (rrow < nrows) {
+                if (rrow < rb_end) {
                     const int y = y0 + rrow % ny, z = z0 + rrow / ny;
                     float lo = A.g.oy + (float)y * hc, hi = lo + hc;
                     float pad = (fabsf(A.g.oy) + fabsf(hi) + hc) * 4e-6f;
@@ -721,9 +771,42 @@ k_gate(GateArgs A)
             if (q2n > 0) stage_b(q2n);
             flush();
         }
-        if (lane == 0) {
-            A.pair_cnt_s[t] = total_out;
-            if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
+        if (!HEAVY) {
+            if (lane == 0) {
+                A.pair_cnt_s[t] = total_out;
+                if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
+            }
+        } else {
+            // the segment's count; the warp that finishes the parent's last segment turns the counts into offsets
+            // (segment order = row order, so the parent's CSR order does not depend on scheduling)
+            uint32_t prev = 0;
+            if (lane == 0) {
+                A.seg_cnt[seg_id] = total_out;
+                __threadfence();
+                prev = atomicAdd(&A.seg_done[t], 1u);
+            }
+            prev = __shfl_sync(full, prev, 0);
+            if (prev == seg_n - 1) {
+                __threadfence();
+                uint32_t run = 0;
+                for (uint32_t b = 0; b < seg_n; b += 32) {
+                    const uint32_t k = b + lane;
+                    const uint32_t c = k < seg_n ? __ldcg(&A.seg_cnt[seg_first + k]) : 0u;
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(full, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (k < seg_n) A.seg_off[seg_first + k] = run + incl - c;
+                    run += __shfl_sync(full, incl, 31);
+                }
+                if (lane == 0) {
+                    A.pair_cnt_s[t] = run;
+                    if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = run;
+                    A.seg_done[t] = 0u;
+                }
+            }
         }
         __syncwarp();
       }
@@ -739,28 +822,33 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long lon
                              unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
                              const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s,
                              const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c, uint2* __restrict__ claims,
-                             uint4* __restrict__ ovf, unsigned long long ovf_cap)
+                             uint4* __restrict__ ovf, unsigned long long ovf_cap, const uint32_t* __restrict__ seg_off)
 {
     pdl_enter();
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
     const int lane = threadIdx.x & 31;
-    const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    // launched over the chunk capacity; the number of chunks written is read on the device
+    // the number of chunks written is read on the device; the grid is sized by the host's upper bound and capped, warps
+    // stride over the chunks (a launch over the whole capacity spent most of its time on warps with nothing to do)
     const unsigned long long nchunks = min(counters[C_POOL] >> POOL_BITS, chunk_cap);
-    if (c >= nchunks) return;
-    const uint4 ch = chunks[c];
-    const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
-    const uint32_t srank = claims ? ptab[ch.x].y : 0u;
-    for (uint32_t k = lane; k < ch.z; k += 32) {
-        const uint2 p = pool[(size_t)ch.y + k];
-        csr_s[dst + k] = p;
-        if (claims) {
-            const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
-            if (slot < (uint32_t)CLAIM_K) {
-                claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
-            } else {
-                const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
-                if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nchunks; c += nwarps) {
+        uint4 ch = chunks[c];
+        // a chunk of a heavy parent's segment carries the segment (index + 1) above the count: its prefix is relative to the segment
+        if (ch.z >> 8) ch.w += seg_off[(ch.z >> 8) - 1u];
+        ch.z &= 0xffu;
+        const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
+        const uint32_t srank = claims ? ptab[ch.x].y : 0u;
+        for (uint32_t k = lane; k < ch.z; k += 32) {
+            const uint2 p = pool[(size_t)ch.y + k];
+            csr_s[dst + k] = p;
+            if (claims) {
+                const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
+                if (slot < (uint32_t)CLAIM_K) {
+                    claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
+                } else {
+                    const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+                    if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
+                }
             }
         }
     }
@@ -907,10 +995,10 @@ __global__ void k_segsum(const uint32_t* __restrict__ key, const float* __restri
 //   parent boundary        : normalise, det, flag, validity, one 64-byte + one SH row store
 // ---------------------------------------------------------------------------
 #ifndef HEM_MOM_U
-#define HEM_MOM_U 8
+#define HEM_MOM_U 4
 #endif
 #ifndef HEM_MOM_MINB
-#define HEM_MOM_MINB 1
+#define HEM_MOM_MINB 4
 #endif
 constexpr int MOM_WARPS = 8;
 constexpr int MOM_B = HEM_MOM_B;

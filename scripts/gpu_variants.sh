@@ -1,9 +1,7 @@
 #!/bin/bash
-for lib in "" scratch/libhem_GATE_TB_2.so scratch/libhem_GATE_TB_8.so scratch/libhem_MOM_B_4.so scratch/libhem_MOM_B_16.so; do
-  echo "#### lib=$lib"
-  HEM_B200_LIB=$([ -n "$lib" ] && echo $PWD/$lib) python - <<'PY'
-import sys; sys.path.insert(0,'.')
-from scripts.gpu_check import timing
-timing(1_000_000, 5000, 5, reps=3)
-PY
+# time alternative builds of the library (libhem_v_*.so) on the 3M / 1M pyramids: level-0/1 kernel times
+mkdir -p gpurun_out
+for lib in libhem_b200.so "$@"; do
+  echo "=== $lib"
+  HEM_B200_LIB=$PWD/gaussiansplattingregistration_b200/$lib timeout 300 python scripts/gpu_base3m.py 2>&1 | grep -E "step [01]:|pyramid" | sed -E 's/.*n_in ([0-9]+).*gate ([0-9.]+) \(k ([0-9.]+)\).*mom ([0-9.]+) \(k ([0-9.]+)\).*/n \1 gate \2 k_gate \3 mom \4 k_mom \5/' | tee -a gpurun_out/variants.log
 done

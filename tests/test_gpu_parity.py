@@ -673,3 +673,30 @@ def test_gpu_heavy_parent_moments_path(port):
         err_heavy = np.abs(a["weight"] / w64 - 1.0).max()
         err_plain = np.abs(d["weight"] / w64 - 1.0).max()
         assert err_heavy <= err_plain and err_heavy < 2e-5, (err_heavy, err_plain)
+
+
+def test_gpu_heavy_parent_gate_path(port):
+    """Parents whose search box spans many
+    rows of cells are scanned by the whole grid in segments of 64 rows (k_gate<true>) instead of by one warp.  With the
+    row threshold forced down on a heavy-tailed cloud a good share of the parents goes that way: child sets, counts and
+    masks must equal the oracle's exactly, values within tolerance, results bit-identical run to run and — because the
+    segment order is the row order — bit-identical to the one-warp path as well."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(20000, seed=321, density=8000.0, sh_degree=1, scale_sigma_ln=1.0, clip_sigma=None)
+    r = port.run(*c.arrays(), levels=1, seed=23)
+    with HemContext(0, seed=23) as ctx:
+        ctx.set_option("keep_pairs", 1)
+        ctx.set_option("heavy_rows", 0)
+        ctx.build(*c.arrays(), cluster_level=1)
+        plain = ctx.level(1, True)
+        ctx.set_option("heavy_rows", 64)
+        ctx.build(*c.arrays(), cluster_level=1)                 # first deferred parent reported -> step redone with the split
+        a = ctx.level(1, True)
+        gp, pc = ctx.step_pairs(0), r.children(0)
+        assert_children_equal(gp["parent_idx"], gp["off"], gp["child"], pc["parent_idx"], pc["off"], pc["child"], what="heavy gate")
+        assert_level_close(a, r.level(1), what="heavy gate vs oracle")
+        ctx.build(*c.arrays(), cluster_level=1)
+        b = ctx.level(1, True)
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), f"{k} differs run to run"
+            assert np.array_equal(a[k], plain[k], equal_nan=True), f"{k} differs from the one-warp path"
