@@ -38,6 +38,7 @@ SIGNATURES = {
     "hem_level_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "hem_level_registration_inputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hem_level_from_mixture": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hem_icp_point_to_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
                                          C.c_double, C.c_double, C.c_int, _d, C.c_void_p]),
     "hem_icp_multiscale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _d, C.POINTER(C.c_int32), C.c_double, C.c_double,

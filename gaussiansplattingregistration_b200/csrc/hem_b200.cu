@@ -1367,6 +1367,40 @@ int hem_level_registration_inputs(hem_ctx* ctx, int level, double* points, doubl
     return HEM_OK;
 }
 
+int hem_level_from_mixture(hem_ctx* ctx, int level, float* scaling, float* rotation, float* eigenvalues, float* eigenvectors)
+{
+    if (!ctx) return HEM_ERR_INVALID;
+    if (level < 0 || level > (int)ctx->stats.size() || (size_t)level >= ctx->levels.size()) { ctx->err = "level not built"; return HEM_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Level& L = ctx->levels[level];
+    const int64_t n = L.n;
+    if (n == 0) return HEM_OK;
+    float* outs[4] = { scaling, rotation, eigenvalues, eigenvectors };
+    const size_t per[4] = { 12, 16, 12, 36 };
+    DevBuf* stage[4] = { &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d };
+    float* dev[4];
+    bool staged[4];
+    for (int k = 0; k < 4; ++k) {
+        staged[k] = false;
+        dev[k] = outs[k];
+        if (outs[k] && !is_device_ptr(outs[k])) {
+            CKR(ensure(ctx, *stage[k], (size_t)n * per[k]));
+            dev[k] = stage[k]->as<float>();
+            staged[k] = true;
+        }
+    }
+    k_from_mixture<<<blocks_for(n, 128), 128, 0, st>>>(L.geo.as<float4>(), n, dev[0], dev[1], dev[2], dev[3]);
+    CK(cudaGetLastError()); ctx->n_launches++;
+    for (int k = 0; k < 4; ++k)
+        if (staged[k]) {
+            CK(cudaMemcpyAsync(outs[k], dev[k], (size_t)n * per[k], cudaMemcpyDeviceToHost, st));
+            ctx->bytes_d2h += (size_t)n * per[k];
+        }
+    CK(cudaStreamSynchronize(st));
+    return HEM_OK;
+}
+
 int hem_bind_output(hem_ctx* ctx, int level, float* xyz, float* color, float* opacity, float* cov6, float* sh,
                     int64_t capacity_rows)
 {

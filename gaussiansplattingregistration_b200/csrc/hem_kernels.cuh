@@ -228,6 +228,101 @@ __global__ void k_registration_inputs(const float4* __restrict__ geo, int64_t n,
 }
 
 // ---------------------------------------------------------------------------
+// "Next" row (second half): what GaussianModel.from_mixture derives from a level's covariances
+// (src/models/gaussian_model.py:141-153 -> decompose_covariance_matrix :242-265 -> matrices_to_quaternions,
+// src/utils/general_utils.py:94-100), one thread per component:
+//   * eigen-decomposition of the symmetric 3x3 covariance (torch.linalg.eigh there; cyclic Jacobi in FP64 here),
+//     eigenvalues ascending, eigenvectors as columns, sign fixed so that the largest-magnitude component of every
+//     eigenvector is positive (eigh leaves the sign to the LAPACK / cuSOLVER build: the reference's own output is
+//     defined only up to these signs);
+//   * the reference's axis-correspondence reorder AS WRITTEN: corr[i] = argmax_j |V[j][i]| (the axis eigenvector i
+//     points along, first maximum), sorted_eigenvalues[corr[i]] = eigenvalues[i], and ROW i of V goes to row corr[i]
+//     (the reference scatters rows of the eigenvector matrix, not columns); a slot no eigenvector maps to stays 0,
+//     of two eigenvectors mapping to the same axis the later one wins;
+//   * `scaling` = the reordered eigenvalues (variances, not standard deviations — as in the reference);
+//   * `rotation` = (w, x, y, z) with w = sqrt(1 + trace)/2, x = (R21 - R12)/(4w), ... evaluated in FP32.
+// ---------------------------------------------------------------------------
+__global__ void k_from_mixture(const float4* __restrict__ geo, int64_t n, float* __restrict__ scaling,
+                               float* __restrict__ rotation, float* __restrict__ evals, float* __restrict__ evecs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q1 = geo[4 * i + 1], q2 = geo[4 * i + 2];
+    double a[3][3] = { { q1.x, q1.y, q1.z }, { q1.y, q1.w, q2.x }, { q1.z, q2.x, q2.y } };
+    double v[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (!(off > 0.0)) break;                         // diagonal (or NaN): done
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const double apq = a[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                // A <- A J
+                const double akp = a[k][p], akq = a[k][q];
+                a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                // A <- J^T A
+                const double apk = a[p][k], aqk = a[q][k];
+                a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                // V <- V J
+                const double vkp = v[k][p], vkq = v[k][q];
+                v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq;
+            }
+        }
+    }
+    // ascending eigenvalues, columns permuted alongside
+    double lam[3] = { a[0][0], a[1][1], a[2][2] };
+    int ord[3] = { 0, 1, 2 };
+#define HEM_SW(x, y) { if (lam[ord[y]] < lam[ord[x]]) { const int t_ = ord[x]; ord[x] = ord[y]; ord[y] = t_; } }
+    HEM_SW(0, 1) HEM_SW(1, 2) HEM_SW(0, 1)
+#undef HEM_SW
+    float V[3][3], L[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int o = ord[c];
+        L[c] = (float)lam[o];
+        double x = v[0][o], y = v[1][o], z = v[2][o];
+        const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+        const double lead = (ax >= ay && ax >= az) ? x : (ay >= az ? y : z);
+        if (lead < 0.0) { x = -x; y = -y; z = -z; }
+        V[0][c] = (float)x; V[1][c] = (float)y; V[2][c] = (float)z;
+    }
+    if (evals) { evals[3 * i] = L[0]; evals[3 * i + 1] = L[1]; evals[3 * i + 2] = L[2]; }
+    if (evecs)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) evecs[9 * i + 3 * r + c] = V[r][c];
+    // the reference's reorder (gaussian_model.py:252-263)
+    float SL[3] = { 0.0f, 0.0f, 0.0f }, R[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        int corr = 0;
+        float best = fabsf(V[0][e]);
+        if (fabsf(V[1][e]) > best) { best = fabsf(V[1][e]); corr = 1; }
+        if (fabsf(V[2][e]) > best) { corr = 2; }
+        SL[corr] = L[e];
+        R[corr][0] = V[e][0]; R[corr][1] = V[e][1]; R[corr][2] = V[e][2];
+    }
+    if (scaling) { scaling[3 * i] = SL[0]; scaling[3 * i + 1] = SL[1]; scaling[3 * i + 2] = SL[2]; }
+    if (rotation) {
+        const float w = sqrtf(1.0f + (R[0][0] + R[1][1] + R[2][2])) / 2.0f;
+        rotation[4 * i] = w;
+        rotation[4 * i + 1] = (R[2][1] - R[1][2]) / (4.0f * w);
+        rotation[4 * i + 2] = (R[0][2] - R[2][0]) / (4.0f * w);
+        rotation[4 * i + 3] = (R[1][0] - R[0][1]) / (4.0f * w);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // S1: parent radii + statistics.  mixture.cpp:70-95
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -233,6 +233,34 @@ class HemContext:
             C.c_void_p(out["normals"].ctypes.data) if normals else None))
         return out
 
+    def from_mixture(self, level: int, sh_degree: int | None = None, decomposition: bool = False) -> dict:
+        """The attributes GaussianModel.from_mixture builds from a mixture level (reference
+        src/models/gaussian_model.py:141-153), as torch CUDA tensors with the reference's names and shapes:
+        `_xyz` [n,3], `_features_dc` [n,1,3], `_features_rest` [n,(deg+1)^2-1,3], `_opacity` [n] (1-D, as in the
+        reference), `_covariance` [n,6], `_scaling` [n,3] and `_rotation` [n,4] from the GPU eigen-decomposition
+        (``hem_level_from_mixture``; the reference runs torch.linalg.eigh + Python scatter code here)."""
+        import torch
+        d = self.level_torch(level)
+        n, F = d["xyz"].shape[0], self.sh_floats
+        if sh_degree is None:
+            sh_degree = int(round((F // 3 + 1) ** 0.5)) - 1
+        if 3 * ((sh_degree + 1) ** 2 - 1) != F:
+            raise ValueError(f"sh_degree {sh_degree} does not match {F} SH floats per splat")
+        dev = d["xyz"].device
+        scaling = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        rotation = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        ev = torch.empty((n, 3), dtype=torch.float32, device=dev) if decomposition else None
+        evec = torch.empty((n, 3, 3), dtype=torch.float32, device=dev) if decomposition else None
+        self._check(self._lib.hem_level_from_mixture(
+            self._h, level, C.c_void_p(scaling.data_ptr()), C.c_void_p(rotation.data_ptr()),
+            C.c_void_p(ev.data_ptr()) if decomposition else None, C.c_void_p(evec.data_ptr()) if decomposition else None))
+        out = dict(sh_degree=sh_degree, _xyz=d["xyz"], _features_dc=d["colors"].view(-1, 1, 3),
+                   _features_rest=d["sh"].view(n, (sh_degree + 1) ** 2 - 1, 3), _opacity=d["opacity"],
+                   _covariance=d["cov6"], _scaling=scaling, _rotation=rotation)
+        if decomposition:
+            out["eigenvalues"], out["eigenvectors"] = ev, evec
+        return out
+
     def icp(self, source, target, init=None, max_correspondence: float = 5.0, relative_fitness: float = 1e-6,
             relative_rmse: float = 1e-6, max_iteration: int = 30, with_correspondences: bool = False) -> "IcpResult":
         """Point-to-point ICP on the GPU with Open3D's definitions (``hem_icp_point_to_point``; replaces

@@ -126,6 +126,16 @@ int hem_level_copy(hem_ctx* ctx, int level,
 int hem_level_registration_inputs(hem_ctx* ctx, int level, double* points, double* colors, double* cov33,
                                   double* normals);
 
+/* What GaussianModel.from_mixture derives from a level's covariances on the GPU
+ * (src/models/gaussian_model.py:141-153, decompose_covariance_matrix :242-265, matrices_to_quaternions
+ * src/utils/general_utils.py:94-100): `scaling` [n,3] = eigenvalues after the reference's axis-correspondence
+ * reorder, `rotation` [n,4] = (w,x,y,z) of the reordered eigenvector matrix, exactly as the reference writes them
+ * (rows scattered, variances not standard deviations).  Optional `eigenvalues` [n,3] (ascending) and
+ * `eigenvectors` [n,3,3] (columns, largest-magnitude component positive) expose the decomposition itself; the
+ * reference's torch.linalg.eigh leaves the eigenvector signs to the backend, so `rotation` agrees with it up to
+ * those signs.  Any pointer may be NULL; host or device memory. */
+int hem_level_from_mixture(hem_ctx* ctx, int level, float* scaling, float* rotation, float* eigenvalues, float* eigenvectors);
+
 /* "Next" row: the consumer of the pyramid.  Point-to-point ICP with the definitions of
  * the Open3D call the reference makes per level — replaces
  *   o3d.pipelines.registration.registration_icp(source, target, max_correspondence, init,
