@@ -113,6 +113,12 @@ struct hem_ctx {
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
     cudaEvent_t ev[EV_COUNT] = {};
 
+    // independent stages of a step run beside the main chain on a second stream (fork / join by events):
+    // control-block reset + parent-rank scan beside the grid build, orphan scan + copy beside the moment kernel
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;
+    DevBuf cubtmp2;                              // CUB temp storage of the second stream
     // copy/compute overlap: SH rows arrive and finished levels leave on a second stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_geo = nullptr, ev_sh = nullptr, ev_level = nullptr;
@@ -260,22 +266,24 @@ int bits_for(uint64_t max_value)
     return b;
 }
 
-template <class F> int cub_call(hem_ctx* ctx, F&& f)
+template <class F> int cub_call(hem_ctx* ctx, DevBuf& tmp, F&& f);
+template <class F> int cub_call(hem_ctx* ctx, F&& f) { return cub_call(ctx, ctx->cubtmp, std::forward<F>(f)); }
+template <class F> int cub_call(hem_ctx* ctx, DevBuf& tmp, F&& f)
 {
     // CUB's two-phase protocol costs a second host-side dispatch per call, which matters on the
     // small (launch-bound) levels: with a warm temp buffer the call goes straight through and the
     // size query only runs if CUB reports the buffer as too small.
-    if (ctx->cubtmp.p && ctx->cubtmp.cap >= (size_t)8 << 20) {
-        size_t have = ctx->cubtmp.cap;
-        cudaError_t e = f(ctx->cubtmp.p, have);
+    if (tmp.p && tmp.cap >= (size_t)8 << 20) {
+        size_t have = tmp.cap;
+        cudaError_t e = f(tmp.p, have);
         if (e == cudaSuccess) return HEM_OK;
         cudaGetLastError();
     }
     size_t bytes = 0;
     CK(f((void*)nullptr, bytes));
-    CKR(ensure(ctx, ctx->cubtmp, std::max<size_t>(bytes, (size_t)8 << 20)));
-    size_t have = ctx->cubtmp.cap;
-    CK(f(ctx->cubtmp.p, have));
+    CKR(ensure(ctx, tmp, std::max<size_t>(bytes, (size_t)8 << 20)));
+    size_t have = tmp.cap;
+    CK(f(tmp.p, have));
     return HEM_OK;
 }
 
@@ -466,7 +474,16 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, PFLAG, n * 4));
     }
     CKR(ensure(ctx, ctx->prank, n * 4));
-    pdl(k_zero, (unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st)(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
+    // fork 1 (levels whose prep was carried over): the control-block reset and the parent-rank scan do not depend on
+    // the grid build and run beside it on the second stream; the main chain joins before the first kernel that needs them
+    const bool fork1 = carried && ctx->overlap && ctx->aux_stream;
+    cudaStream_t s1 = fork1 ? ctx->aux_stream : st;
+    bool join1_pending = false;
+    if (fork1) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    }
+    pdl(k_zero, (unsigned)std::min<size_t>((ctl_bytes / 16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, s1)(ctx->ctlbuf.as<uint4>(), ctl_bytes / 16);
     CK(cudaGetLastError()); ctx->n_launches++;
     Ctl ps;
     if (carried) {
@@ -482,9 +499,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         ps = *ctx->h_ctl;
     }
     ctx->prep_valid = false;
-    CKR(cub_call(ctx, [&](void* t, size_t& b) {
-        return cub::DeviceScan::ExclusiveSum(t, b, PFLAG.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, st);
+    CKR(cub_call(ctx, fork1 ? ctx->cubtmp2 : ctx->cubtmp, [&](void* t, size_t& b) {
+        return cub::DeviceScan::ExclusiveSum(t, b, PFLAG.as<uint32_t>(), ctx->prank.as<uint32_t>(), (int)n, s1);
     }));
+    if (fork1) { CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream)); join1_pending = true; }
+    auto join1 = [&]() -> int {
+        if (join1_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); join1_pending = false; }
+        return HEM_OK;
+    };
     const int64_t np = (int64_t)ps.n_parents;
     S.n_parents = np;
     S.n_certified = (int64_t)ps.n_certified;
@@ -507,6 +529,30 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     size_t pool_cap_used = 0, chunk_cap_final = 0;
     const bool have_pairs = np > 0;   // parents without a usable radius simply find no child
     bool launched_heavy = false, launched_gate_heavy = false;
+    // fork 2: the orphans (mixture.cpp:251-253) depend on sumLw only; their scan and copy run beside the moment kernel
+    // on the second stream and are joined in front of k_finish
+    bool fork2 = false;
+    auto orphan_stage = [&]() -> int {
+        CKR(ensure(ctx, ctx->orank, n * 4));
+        fork2 = ctx->overlap && ctx->aux_stream && !(ctx->sh_pending && ctx->sh_gather_chunk > 0);
+        cudaStream_t s2 = fork2 ? ctx->aux_stream : st;
+        if (fork2) {
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            if (ctx->sh_pending) CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_sh, 0));    // level-0 SH rows still arriving
+        } else if (ctx->sh_pending) {
+            CKR(wait_sh(ctx));
+        }
+        CKR(cub_call(ctx, fork2 ? ctx->cubtmp2 : ctx->cubtmp, [&](void* t, size_t& b) {
+            cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
+            return cub::DeviceScan::ExclusiveSum(t, b, it, ctx->orank.as<uint32_t>(), (int)n, s2);
+        }));
+        pdl(k_orphans, blocks_for(n, 256), 256, 0, s2)(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
+                                                       (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
+        CK(cudaGetLastError()); ctx->n_launches++;
+        if (fork2) CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        return HEM_OK;
+    };
     if (have_pairs) {
         // ---- S2 grid --------------------------------------------------------------------------
         GridP g;
@@ -582,6 +628,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             return cub::DeviceSelect::Flagged(t, b, thrust::counting_iterator<uint32_t>(0), ctx->sflag.as<uint8_t>(),
                                               ctx->psorted.as<uint32_t>(), ctx->nsel.as<uint32_t>(), (int)n, st);
         }));
+        CKR(join1());
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
@@ -803,6 +850,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CK(cudaGetLastError()); ctx->n_launches++;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+        CKR(orphan_stage());
 
         // ---- S4 moments -------------------------------------------------------------------------------
         MomArgs M;
@@ -870,23 +918,19 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                                       out.sh.as<float>());
             CK(cudaGetLastError()); ctx->n_launches++;
         }
-    } else if (ctx->timing) {
-        CK(cudaEventRecord(ctx->ev[EV_GRID], st));
-        CK(cudaEventRecord(ctx->ev[EV_GATE], st));
-        CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+    } else {
+        CKR(join1());
+        if (ctx->timing) {
+            CK(cudaEventRecord(ctx->ev[EV_GRID], st));
+            CK(cudaEventRecord(ctx->ev[EV_GATE], st));
+            CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+        }
+        CKR(orphan_stage());
     }
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
 
-    // ---- S5 orphans + filter ---------------------------------------------------------------------------
-    if (ctx->sh_pending) CKR(wait_sh(ctx));
-    CKR(ensure(ctx, ctx->orank, n * 4));
-    CKR(cub_call(ctx, [&](void* t, size_t& b) {
-        cub::TransformInputIterator<uint32_t, IsOrphan, const float*> it(d_sumlw, IsOrphan());
-        return cub::DeviceScan::ExclusiveSum(t, b, it, ctx->orank.as<uint32_t>(), (int)n, st);
-    }));
-    pdl(k_orphans, blocks_for(n, 256), 256, 0, st)(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
-                                                   (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
-    CK(cudaGetLastError()); ctx->n_launches++;
+    // ---- S5 filter ---------------------------------------------------------------------------------------
+    if (fork2) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));        // the orphan rows are in place
     // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
     pdl(k_finish, blocks_for(cap_rows, 256), 256, 0, st)(out.geo.as<float4>(), np, ctx->orank.as<uint32_t>(), d_sumlw, n,
@@ -1117,6 +1161,10 @@ hem_ctx* hem_create(int device, uint64_t seed)
     }
     ctx->stream = ctx->own_stream;
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (const char* cs = getenv("HEM_OVERLAP")) ctx->overlap = atoi(cs) != 0;
     cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_sh, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_level, cudaEventDisableTiming);
@@ -1151,6 +1199,9 @@ void hem_destroy(hem_ctx* ctx)
     for (cudaEvent_t e : { ctx->ev_icp0, ctx->ev_icp1 }) if (e) cudaEventDestroy(e);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    for (cudaEvent_t e : { ctx->ev_fork, ctx->ev_join }) if (e) cudaEventDestroy(e);
+    release(ctx->cubtmp2);
     for (cudaEvent_t e : { ctx->ev_geo, ctx->ev_sh, ctx->ev_level }) if (e) cudaEventDestroy(e);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1172,6 +1223,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
+    else if (k == "overlap") ctx->overlap = value != 0;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "shard_upload") ctx->shard_upload = value != 0;

@@ -63,6 +63,12 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
  *   "sumlw_mode"  0 (default) auto, 1 stable radix sort by child, 2 claim table: two bit-identical
  *                 ways of adding a child's claims in ascending parent order
+ *   "overlap"     1 (default) -> stages of a step that do not depend on each other run side by side on a second stream
+ *                 (control-block reset + parent-rank scan beside the grid build, orphan scan + copy beside the moment
+ *                 kernel); 0 -> one chain.  Same results either way.
+ *   "heavy_rows"  a parent whose search box has more rows of cells than max(heavy_rows, heavy_rows_rel x the box of a
+ *                 parent of geometric-mean radius) is scanned by the whole grid in segments instead of by one warp
+ *                 (defaults 128 and 16; heavy_rows = 0: never; single GPU)
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
  *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
  *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own
