@@ -105,9 +105,9 @@ struct hem_ctx {
     DevBuf in_xyz, in_col, in_op, in_cov, in_sh, in_w, in_mask;       // staged host inputs
     DevBuf out_a, out_b, out_c, out_d, out_e, out_f, out_g;           // staged outputs
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
-    DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, sflag, cell_start, psorted;
+    DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, cell_start;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, nsel, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done, seg_info, hv_hdr, seg_cnt, seg_off, seg_done;
+    DevBuf valid, vflag, vpos, cubtmp, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done, seg_info, hv_hdr, seg_cnt, seg_off, seg_done;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
@@ -608,26 +608,21 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->val, n * 4)); CKR(ensure(ctx, ctx->val2, n * 4));
         CKR(ensure(ctx, ctx->sp0, n * 16)); CKR(ensure(ctx, ctx->sp1, n * 16));
         CKR(ensure(ctx, ctx->sp2, n * 16)); CKR(ensure(ctx, ctx->sp3, n * 16));
-        CKR(ensure(ctx, ctx->sflag, n));
-        CKR(ensure(ctx, ctx->cell_start, ((size_t)ncell + 1) * 4));
-        CKR(ensure(ctx, ctx->psorted, np * 4));
-        CKR(ensure(ctx, ctx->nsel, 8));
-        pdl(k_cellkey, blocks_for(n, 256), 256, 0, st)(geo, n, g, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
+        // keys: non-parents by cell, parents by cell behind them (cell id + ncell): one sort puts the parents in their own
+        // cell-ordered block at slots [n - np, n), and `cell_start` of the first ncell cells indexes non-parents only
+        CKR(ensure(ctx, ctx->cell_start, ((size_t)2 * ncell + 1) * 4));
+        pdl(k_cellkey, blocks_for(n, 256), 256, 0, st)(geo, n, g, ncell, ctx->key.as<uint32_t>(), ctx->val.as<uint32_t>());
         CK(cudaGetLastError()); ctx->n_launches++;
-        const int kbits = bits_for(ncell - 1);
+        const int kbits = bits_for((uint64_t)2 * ncell - 1);
         CKR(cub_call(ctx, [&](void* t, size_t& b) {
             return cub::DeviceRadixSort::SortPairs(t, b, ctx->key.as<uint32_t>(), ctx->key2.as<uint32_t>(),
                                                    ctx->val.as<uint32_t>(), ctx->val2.as<uint32_t>(), (int)n, 0, kbits, st);
         }));
         pdl(k_sorted_gather, blocks_for(n, 256), 256, 0, st)(geo, ctx->key2.as<uint32_t>(), ctx->val2.as<uint32_t>(), n,
-                                                             ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
+                                                             2u * ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                              ctx->sp2.as<float4>(), ctx->sp3.as<float4>(),
-                                                             ctx->sflag.as<uint8_t>(), ctx->cell_start.as<uint32_t>());
+                                                             ctx->cell_start.as<uint32_t>());
         CK(cudaGetLastError()); ctx->n_launches++;
-        CKR(cub_call(ctx, [&](void* t, size_t& b) {
-            return cub::DeviceSelect::Flagged(t, b, thrust::counting_iterator<uint32_t>(0), ctx->sflag.as<uint8_t>(),
-                                              ctx->psorted.as<uint32_t>(), ctx->nsel.as<uint32_t>(), (int)n, st);
-        }));
         CKR(join1());
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
 
@@ -643,7 +638,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->ptab, np * 8));
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
-        pdl(k_ptab, blocks_for(np, 256), 256, 0, st)(ctx->psorted.as<uint32_t>(), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
+        pdl(k_ptab, blocks_for(np, 256), 256, 0, st)((uint32_t)(n - np), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
                                                      RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
@@ -669,7 +664,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             GateArgs A;
             A.sp0 = ctx->sp0.as<float4>(); A.sp1 = ctx->sp1.as<float4>(); A.sp2 = ctx->sp2.as<float4>();
             A.sp3 = ctx->sp3.as<float4>(); A.cell_start = ctx->cell_start.as<uint32_t>();
-            A.pinfo = ctx->pinfo.as<float4>(); A.g = g; A.t_begin = (int)tb[R]; A.t_end = (int)tb[R + 1];
+            A.pinfo = ctx->pinfo.as<float4>(); A.nc = (uint32_t)(n - np); A.g = g; A.t_begin = (int)tb[R]; A.t_end = (int)tb[R + 1];
             A.cthr = color_delta * color_delta * 0.5f;           // mixture.cpp:123
             A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
@@ -1185,10 +1180,10 @@ void hem_destroy(hem_ctx* ctx)
     DevBuf* all[] = { &ctx->in_xyz, &ctx->in_col, &ctx->in_op, &ctx->in_cov, &ctx->in_sh, &ctx->in_w, &ctx->in_mask,
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->radius2, &ctx->psafe2, &ctx->pflag2, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
-                      &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->sflag, &ctx->cell_start, &ctx->psorted,
+                      &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->cell_start,
                       &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->nsel, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done, &ctx->seg_info, &ctx->hv_hdr,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done, &ctx->seg_info, &ctx->hv_hdr,
                       &ctx->seg_cnt, &ctx->seg_off, &ctx->seg_done,
                       &ctx->icp_src, &ctx->icp_tgt, &ctx->icp_box, &ctx->icp_key, &ctx->icp_key2, &ctx->icp_val, &ctx->icp_val2,
                       &ctx->icp_rows, &ctx->icp_start, &ctx->icp_part, &ctx->icp_state, &ctx->icp_corr };

@@ -42,7 +42,10 @@ __device__ __forceinline__ void pdl_enter()
 //         q3 = (col.r, col.g, col.b, uint bits: bit0 = is_parent, bit1 = covariance certified for the smd pre-test)
 //   sh  : F floats per component, unpadded (180-byte rows at SH degree 3), exactly the caller's
 //         [N,F] layout: a device-resident input is used in place and levels are copied out by DMA
-// Cell-sorted working set of a step (index = slot in cell order), SoA float4 planes:
+// Cell-sorted working set of a step, SoA float4 planes.  Slots [0, n - np) hold the NON-PARENT components in grid-cell
+// order (what `cell_start` indexes and the gate scans), slots [n - np, n) the parents in grid-cell order (slot of the
+// parent at position t = n - np + t): a parent can only claim non-parents and itself (mixture.cpp:131-133), so a third
+// of the candidates never enters the scan and the parents need no separate selection pass.
 //   sp0 = (mean.x, mean.y, mean.z, bits(canonical index | is_parent << 31))
 //   sp1 = (col.r, col.g, col.b, opacity)
 //   sp2 = (c00, c01, c02, c11)
@@ -461,25 +464,25 @@ k_boxhist(const float4* __restrict__ geo, int64_t n, float lox, float loy, float
 // S2: uniform grid.  Replaces PointIndex::create (pointindex.cpp:55-108): cell
 // keys -> radix sort (CUB, in hem_b200.cu) -> cell-sorted SoA planes + offsets.
 // ---------------------------------------------------------------------------
-__global__ void k_cellkey(const float4* __restrict__ geo, int64_t n, GridP g, uint32_t* __restrict__ key,
+__global__ void k_cellkey(const float4* __restrict__ geo, int64_t n, GridP g, uint32_t ncell, uint32_t* __restrict__ key,
                           uint32_t* __restrict__ val)
 {
     pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 q0 = geo[4 * i];
+    const uint32_t flag = __float_as_uint(geo[4 * i + 3].w) & 1u;
     int cx = cell_axis(q0.x, g.ox, g.inv_h, g.gx);
     int cy = cell_axis(q0.y, g.oy, g.inv_h, g.gy);
     int cz = cell_axis(q0.z, g.oz, g.inv_h, g.gz);
-    key[i] = (uint32_t)((cz * g.gy + cy) * g.gx + cx);
+    key[i] = (uint32_t)((cz * g.gy + cy) * g.gx + cx) + (flag ? ncell : 0u);      // parents behind all non-parents
     val[i] = (uint32_t)i;
 }
 
 __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* __restrict__ skey,
                                 const uint32_t* __restrict__ sval, int64_t n, uint32_t ncell,
                                 float4* __restrict__ sp0, float4* __restrict__ sp1, float4* __restrict__ sp2,
-                                float4* __restrict__ sp3, uint8_t* __restrict__ sflag,
-                                uint32_t* __restrict__ cell_start)
+                                float4* __restrict__ sp3, uint32_t* __restrict__ cell_start)
 {
     pdl_enter();
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,7 +494,6 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
     sp1[j] = make_float4(q3.x, q3.y, q3.z, q2.z);
     sp2[j] = q1;
     sp3[j] = make_float4(q2.x, q2.y, q2.w, __uint_as_float((__float_as_uint(q3.w) >> 1) & 1u));
-    sflag[j] = (uint8_t)flag;
     // segment offsets: cell_start[c] = first slot whose key >= c
     uint32_t lo = (j == 0) ? 0u : skey[j - 1] + 1u;
     if (j == 0 || key != skey[j - 1])
@@ -536,6 +538,7 @@ struct GateArgs {
     const float4* sp0; const float4* sp1; const float4* sp2; const float4* sp3;
     const uint32_t* cell_start;
     const float4* pinfo;         // [np * PINFO_F4]
+    uint32_t nc;                 // non-parents of the level = slot of the first parent
     GridP g;
     int t_begin, t_end;          // this rank's slab of parents (cell order)
     int tb;                      // parents per work ticket (1..GATE_TB)
@@ -569,7 +572,7 @@ __device__ __forceinline__ void cell_range(float q, float rr, float o, float inv
     hi = cell_axis(q + (rr + pad), o, inv_h, g);
 }
 
-__global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __restrict__ sp0,
+__global__ void k_ptab(uint32_t nc, const float4* __restrict__ sp0,
                        const float4* __restrict__ sp1, const float4* __restrict__ sp2,
                        const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
                        const float* __restrict__ radius, const uint8_t* __restrict__ psafe,
@@ -579,7 +582,7 @@ __global__ void k_ptab(const uint32_t* __restrict__ psorted, const float4* __res
     pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= np) return;
-    const uint32_t pj = psorted[t];
+    const uint32_t pj = nc + (uint32_t)t;           // parents follow the nc non-parents, in cell order
     const float4 p0 = sp0[pj], p2 = sp2[pj], p3 = sp3[pj];
     const uint32_t s = __float_as_uint(p0.w) & 0x7fffffffu;
     const uint32_t srank = prank[s];
@@ -778,6 +781,14 @@ k_gate(GateArgs A)
                     continue;
                 }
             }
+            // The parent itself is its own first candidate (the grid holds non-parents only): the reference's radius
+            // test sees distance 0 < r*r, the parent-exclusion test lets the parent through (mixture.cpp:131-133), and
+            // the colour / KLD gates are evaluated on it like on any other candidate.
+            if (r2 > 0.0f && (!HEAVY || seg_local == 0u)) {
+                if (lane == 0) q[0] = A.nc + (uint32_t)t;
+                qn = 1;
+                __syncwarp();
+            }
             const int rb_begin = HEAVY ? (int)seg_local * GATE_SEG_ROWS : 0;
             const int rb_end = HEAVY ? min(nrows, rb_begin + GATE_SEG_ROWS) : nrows;
 
@@ -843,10 +854,10 @@ k_gate(GateArgs A)
                     }
                     bool in = false;
                     if (tt < total) {
-                        const uint32_t w = __float_as_uint(c0.w);
-                        // radius test, pointindex.cpp:138 (query - point); parent exclusion, mixture.cpp:131-133
+                        // radius test, pointindex.cpp:138 (query - point); the scanned slots hold non-parents only, so the
+                        // parent exclusion of mixture.cpp:131-133 has nothing to reject here
                         const float d2 = sqdist3(p0.x, p0.y, p0.z, c0.x, c0.y, c0.z);
-                        in = (d2 < r2) && !((w >> 31) && ((w & 0x7fffffffu) != s));
+                        in = d2 < r2;
                     }
                     const unsigned m = __ballot_sync(full, in);
                     if (in) q[qn + __popc(m & ((1u << lane) - 1u))] = jj;
