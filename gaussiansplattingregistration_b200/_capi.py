@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HEM_B200_LIB") or os.path.join(_HERE, "libhem_b200.so")   # override: kernel experiments only
 
-STEP_STATS_LEN = 23
+STEP_STATS_LEN = 24
 ICP_RESULT_LEN = 24
 NCCL_ID_BYTES = 128
 

@@ -9,6 +9,7 @@
 #include "hem_icp.cuh"
 
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX v3: ranges per stage for nsys / ncu --nvtx, no link dependency
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
@@ -23,6 +24,17 @@
 using namespace hem;
 
 namespace {
+
+// NVTX range over a stage of a step (SURVEY.md §5 tracing hook); free when no profiler is attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+struct NvtxMark {      // consecutive stages inside one function: each mark closes the previous range
+    bool open = false;
+    void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+    ~NvtxMark() { if (open) nvtxRangePop(); }
+};
 
 struct NcclId { char internal[128]; };
 
@@ -46,6 +58,7 @@ struct StepStats {
     int64_t n_in = 0, n_parents = 0, n_pairs = 0, n_orphans = 0, n_dropped = 0, n_out = 0, grid_cells = 0, n_certified = 0;
     int64_t n_parents_local = 0, n_pairs_local = 0;   // this rank's share of the gate / moment work (multi-GPU)
     int shards = 1;                                   // ranks the step was sharded over
+    bool tight = false;                               // ellipsoid boxes were used
     double cell_size = 0, max_radius = 0;
     double ms_host = 0;       // host time spent enqueueing the step (up to its closing sync)
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
@@ -67,6 +80,7 @@ struct hem_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     bool timing = false, keep_pairs = false, smd_prefilter = true;
+    bool tight_box = true;         // certified parents search the box of their Mahalanobis ellipsoid when no component of the level is uncertified
     int sumlw_mode = 0;            // 0 auto, 1 radix sort, 2 claim table
     // prep of the next level carried over from k_finish (no prep kernel, no host sync)
     bool prep_valid = false;
@@ -86,7 +100,7 @@ struct hem_ctx {
     // the same for the gate, by rows of cells of the search box: a parent whose box has more rows than
     // max(heavy_rows, heavy_rows_rel x the box of a parent of geometric-mean radius) is scanned by the grid in
     // segments of GATE_SEG_ROWS rows instead of by one warp (heavy_rows = 0: never)
-    int heavy_rows = 128;
+    int heavy_rows = 1024;
     double heavy_rows_rel = 16.0;
     bool heavy_gate_hint = false;
     double cell_scale = 0.55;
@@ -436,6 +450,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     S = StepStats();
     S.n_in = n;
     const auto host_t0 = std::chrono::steady_clock::now();
+    char nvtx_name[48];
+    snprintf(nvtx_name, sizeof nvtx_name, "hem.step level %d (n=%lld)", l, (long long)in.n);
+    NvtxRange nvtx_step(nvtx_name);
+    NvtxMark nvtx;
+    nvtx.next("S1 prep");
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_BEGIN], st));
 
     if (n == 0) { out.n = 0; return HEM_OK; }
@@ -555,6 +574,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     };
     if (have_pairs) {
         // ---- S2 grid --------------------------------------------------------------------------
+        nvtx.next("S2 grid");
         GridP g;
         {
             float bmin[3], bmax[3];
@@ -627,6 +647,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
+        nvtx.next("S3 gate");
         // levels below shard_min_n are not worth an exchange: every rank builds them whole (identical results)
         const int G = (ctx->world > 1 && n >= ctx->shard_min_n) ? ctx->world : 1;
         const int R = G > 1 ? ctx->rank : 0;
@@ -638,9 +659,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
         CKR(ensure(ctx, ctx->ptab, np * 8));
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
+        // ellipsoid boxes (k_ptab): only while the certified pre-test is active and every component can be pre-tested
+        const float kthr_ = distance_delta * distance_delta * 0.5f;
+        const bool pretest = ctx->smd_prefilter && kthr_ <= 1e4f;
+        const float s_box = (ctx->tight_box && pretest && ps.n_uncert == 0) ? (2.0f * kthr_ + 0.5f) / 0.99f * 1.001f : 0.0f;
+        S.tight = s_box > 0.0f;
         pdl(k_ptab, blocks_for(np, 256), 256, 0, st)((uint32_t)(n - np), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, ctx->ptab.as<uint2>(),
+                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, s_box, ctx->ptab.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
         size_t pool_cap = std::max<size_t>(std::max<size_t>(ctx->pool.cap / 8, ctx->pool_min), std::max<size_t>((size_t)8 * n / G, 1 << 16));
@@ -805,6 +831,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
+        nvtx.next("S3 sumLw");
         // sparse regime (the benchmark's): claim table, 2 launches; dense regime: stable radix sort of the
         // canonical CSR by child.  Both add a child's claims in ascending parent rank (bit-identical).
         const bool need_canon = !use_claims || ctx->keep_pairs;
@@ -848,6 +875,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         CKR(orphan_stage());
 
         // ---- S4 moments -------------------------------------------------------------------------------
+        nvtx.next("S4 moments");
         MomArgs M;
         M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = ctx->ptab.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
         M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = d_sumlw;
@@ -925,6 +953,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
 
     // ---- S5 filter ---------------------------------------------------------------------------------------
+    nvtx.next("S5 finish");
     if (fork2) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));        // the orphan rows are in place
     // determinant, fresh flag and validity of every pre-filter row: launched over the row capacity,
     // the actual row count is read on the device, so one host sync closes the step
@@ -1019,7 +1048,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         Ctl& nx = ctx->prep_stats;
         for (int a = 0; a < 3; ++a) { nx.bbmax_u[a] = hc.nx_bbmax_u[a]; nx.bbmin_c[a] = hc.nx_bbmin_c[a]; }
         nx.max_radius_bits = hc.nx_max_radius_bits; nx.n_radius = hc.nx_n_radius; nx.n_parents = hc.nx_n_parents;
-        nx.n_certified = hc.nx_n_certified; nx.sum_radius_fx = hc.nx_sum_radius_fx;
+        nx.n_certified = hc.nx_n_certified; nx.sum_radius_fx = hc.nx_sum_radius_fx; nx.n_uncert = hc.nx_n_uncert;
     }
     if (ctx->timing) {
         CK(cudaEventRecord(ctx->ev[EV_END], st));
@@ -1217,6 +1246,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     if (k == "timing") ctx->timing = value != 0;
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
+    else if (k == "tight_box") ctx->tight_box = value != 0;
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "overlap") ctx->overlap = value != 0;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
@@ -1238,6 +1268,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
                       const uint8_t* level0_parent_mask)
 {
     if (!ctx) return HEM_ERR_INVALID;
+    NvtxRange nvtx_build("hem_build_pyramid");
     ctx->err.clear();
     if (n < 0 || sh_floats < 0 || sh_floats > 256) { ctx->err = "n must be >= 0 and 0 <= sh_floats <= 256"; return HEM_ERR_INVALID; }
     if (n > 0 && (!xyz || !color || !opacity || !cov6 || (sh_floats > 0 && !sh))) { ctx->err = "null input array"; return HEM_ERR_INVALID; }
@@ -1476,7 +1507,7 @@ int hem_step_stats(const hem_ctx* ctx, int step, double* out)
     for (int i = 0; i < 9; ++i) out[9 + i] = S.ms[i];
     out[18] = (double)S.n_certified;
     out[19] = S.ms_host;
-    out[20] = (double)S.n_parents_local; out[21] = (double)S.n_pairs_local; out[22] = (double)S.shards;
+    out[20] = (double)S.n_parents_local; out[21] = (double)S.n_pairs_local; out[22] = (double)S.shards; out[23] = S.tight ? 1.0 : 0.0;
     return HEM_OK;
 }
 

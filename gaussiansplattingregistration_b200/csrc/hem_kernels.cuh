@@ -81,6 +81,9 @@ struct Ctl {
     unsigned int nx_bbmin_c[3];
     unsigned int nx_max_radius_bits, nx_n_radius, nx_n_parents, nx_n_certified;
     unsigned long long nx_sum_radius_fx;
+    // components whose covariance is NOT certified for the smd pre-test (hem_math.cuh), this level / next level:
+    // with none of them, certified parents may search the box of their Mahalanobis ellipsoid instead of their sphere
+    unsigned int n_uncert, nx_n_uncert;
 };
 
 // Control block -> mapped pinned host memory.  The host reads step sizes after a stream sync; a DMA
@@ -348,7 +351,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
-    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0;
+    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0, ucount = 0;
     unsigned long long rsum = 0ull;
     const int64_t ntiles = (n + 255) / 256;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -358,6 +361,7 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
         if (i < n) {
             const float4 q0 = geo[4 * i], q3 = geo[4 * i + 3];
             flag = (__float_as_uint(q3.w) & 1u) != 0;
+            ucount += (__float_as_uint(q3.w) & 2u) ? 0u : 1u;
             pflag[i] = flag ? 1u : 0u;
             if (q0.x == q0.x) { const unsigned o = f2u(q0.x); bmax[0] = max(bmax[0], o); bminc[0] = max(bminc[0], ~o); }
             if (q0.y == q0.y) { const unsigned o = f2u(q0.y); bmax[1] = max(bmax[1], o); bminc[1] = max(bminc[1], ~o); }
@@ -406,6 +410,8 @@ k_prep(const float4* __restrict__ geo, int64_t n, float distance_delta, float* _
     rcount = __reduce_add_sync(full, rcount);
     ccount = __reduce_add_sync(full, ccount);
     if (lane == 0 && ccount) atomicAdd(&ctl->n_certified, ccount);
+    ucount = __reduce_add_sync(full, ucount);
+    if (lane == 0 && ucount) atomicAdd(&ctl->n_uncert, ucount);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(full, rsum, o);
     if (lane == 0) {
@@ -576,7 +582,7 @@ __global__ void k_ptab(uint32_t nc, const float4* __restrict__ sp0,
                        const float4* __restrict__ sp1, const float4* __restrict__ sp2,
                        const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
                        const float* __restrict__ radius, const uint8_t* __restrict__ psafe,
-                       const float4* __restrict__ geo, GridP g, int np, uint2* __restrict__ ptab,
+                       const float4* __restrict__ geo, GridP g, int np, float s_box, uint2* __restrict__ ptab,
                        float4* __restrict__ pinfo)
 {
     pdl_enter();
@@ -591,13 +597,25 @@ __global__ void k_ptab(uint32_t nc, const float4* __restrict__ sp0,
     const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
     const Sym3 ip = inverse_sym3(pc, p3.z);
     int y0 = 0, y1 = 0, z0 = 0, z1 = 0;
+    float hx = __uint_as_float(0x7f800000u);          // half-extent of the search box along x (+inf: the sphere's chord decides)
     if (rad > 0.0f) {
         const float rr = rad * 1.00001f;
-        cell_range(p0.y, rr, g.oy, g.inv_h, g.gy, y0, y1);
-        cell_range(p0.z, rr, g.oz, g.inv_h, g.gz, z0, z1);
+        float ry = rr, rz = rr;
+        // Ellipsoid box (s_box > 0: no component of the level is uncertified, and this parent is certified).  The
+        // certified pre-test (hem_math.cuh) rejects every candidate whose squared Mahalanobis distance exceeds
+        // 2*kthr + 0.5 in FP32; with d'P^-1 d >= d_i^2 / P_ii that is every candidate outside the axis-aligned box of
+        // the ellipsoid d'P^-1 d <= s_box, s_box = (2*kthr + 0.5) / 0.99 * 1.001 (the certificate bounds the FP32 value
+        // from below by 0.99 of the exact one).  Searching sphere-box INTERSECT ellipsoid-box leaves membership untouched.
+        if (s_box > 0.0f && psafe[s]) {
+            hx = sqrtf(s_box * p2.x) * 1.0001f;
+            ry = fminf(rr, sqrtf(s_box * p2.w) * 1.0001f);
+            rz = fminf(rr, sqrtf(s_box * p3.y) * 1.0001f);
+        }
+        cell_range(p0.y, ry, g.oy, g.inv_h, g.gy, y0, y1);
+        cell_range(p0.z, rz, g.oz, g.inv_h, g.gz, z0, z1);
     }
     float4* o = pinfo + (size_t)t * PINFO_F4;
-    o[0] = p0; o[1] = sp1[pj]; o[2] = p2; o[3] = p3;
+    o[0] = p0; o[1] = sp1[pj]; o[2] = p2; o[3] = make_float4(p3.x, p3.y, p3.z, hx);
     o[4] = make_float4(rad, geo[4 * (size_t)s].w, __uint_as_float(srank | ((uint32_t)psafe[s] << 31)),
                        __uint_as_float(s));
     o[5] = make_float4(ip.e00, ip.e01, ip.e02, ip.e11);
@@ -767,6 +785,9 @@ k_gate(GateArgs A)
             const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
+            // x range of the ellipsoid box (k_ptab; the whole grid when the parent searches its sphere)
+            int xlo = 0, xhi = A.g.gx - 1;
+            if (p3.w < 3.0e38f) cell_range(p0.x, p3.w, A.g.ox, A.g.inv_h, A.g.gx, xlo, xhi);
             if (!HEAVY) {
                 if (A.row_report > 0 && nrows > A.row_report && lane == 0) atomicAdd(A.n_heavy_gate, 1u);
                 if (A.row_defer > 0 && nrows > A.row_defer) {          // uniform: left to k_gate<true>
@@ -784,7 +805,8 @@ k_gate(GateArgs A)
             // The parent itself is its own first candidate (the grid holds non-parents only): the reference's radius
             // test sees distance 0 < r*r, the parent-exclusion test lets the parent through (mixture.cpp:131-133), and
             // the colour / KLD gates are evaluated on it like on any other candidate.
-            if (r2 > 0.0f && (!HEAVY || seg_local == 0u)) {
+            // (the test is spelled out on the parent's own coordinates: a NaN / infinite mean fails it, as in the reference)
+            if (sqdist3(p0.x, p0.y, p0.z, p0.x, p0.y, p0.z) < r2 && (!HEAVY || seg_local == 0u)) {
                 if (lane == 0) q[0] = A.nc + (uint32_t)t;
                 qn = 1;
                 __syncwarp();
@@ -813,11 +835,13 @@ k_gate(GateArgs A)
                     if (d2yz <= rr2) {
                         const float dxm = sqrtf(fmaxf(rr2 - d2yz, 0.0f)) * 1.00001f;
                         const float padx = (fabsf(p0.x) + dxm) * 2.4e-7f;
-                        const int xa = cell_axis(p0.x - (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx);
-                        const int xb = cell_axis(p0.x + (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx);
-                        const uint32_t base = (uint32_t)((z * A.g.gy + y) * A.g.gx);
-                        ra = A.cell_start[base + xa];
-                        len = A.cell_start[base + xb + 1] - ra;
+                        const int xa = max(cell_axis(p0.x - (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx), xlo);
+                        const int xb = min(cell_axis(p0.x + (dxm + padx), A.g.ox, A.g.inv_h, A.g.gx), xhi);
+                        if (xa <= xb) {
+                            const uint32_t base = (uint32_t)((z * A.g.gy + y) * A.g.gx);
+                            ra = A.cell_start[base + xa];
+                            len = A.cell_start[base + xb + 1] - ra;
+                        }
                     }
                 }
                 uint32_t incl = len;
@@ -1451,7 +1475,7 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
     if (j == 0) ctl->counters[C_NORPH] = (unsigned long long)norph;
     bool bad = false;
     unsigned int bmax[3] = { 0u, 0u, 0u }, bminc[3] = { 0u, 0u, 0u };
-    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0;
+    unsigned int rbits = 0, rcount = 0, pcount = 0, ccount = 0, ucount = 0;
     unsigned long long rsum = 0ull;
     if (j < n) {
         const float4 q0 = geo[4 * j], q1 = geo[4 * j + 1];
@@ -1464,8 +1488,9 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
             geo[4 * j + 2] = q2;
         }
         const bool flag = parent_flag(seed, rng_base + (uint64_t)j, pp);
-        reinterpret_cast<float*>(geo)[16 * j + 15] =
-            __uint_as_float((flag ? 1u : 0u) | (child_cov_certified(cc, dt) ? 2u : 0u));
+        const bool ccert = child_cov_certified(cc, dt);
+        ucount = ccert ? 0u : 1u;
+        reinterpret_cast<float*>(geo)[16 * j + 15] = __uint_as_float((flag ? 1u : 0u) | (ccert ? 2u : 0u));
         bad = (q0.x != q0.x || q0.y != q0.y || q0.z != q0.z) || (dt != dt) || dt <= 0.0f;
         valid[j] = bad ? 0 : 1;
         // next level's S1 (mixture.cpp:70-95), valid as long as nothing gets erased by the filter
@@ -1487,6 +1512,8 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(full, bad);
     if (lane == 0 && m) atomicAdd(&ctl->counters[C_INVALID], (unsigned long long)__popc(m));
+    ucount = __reduce_add_sync(full, ucount);
+    if (lane == 0 && ucount) atomicAdd(&ctl->nx_n_uncert, ucount);
 #pragma unroll
     for (int a = 0; a < 3; ++a) { bmax[a] = __reduce_max_sync(full, bmax[a]); bminc[a] = __reduce_max_sync(full, bminc[a]); }
     rbits = __reduce_max_sync(full, rbits);

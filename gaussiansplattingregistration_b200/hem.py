@@ -16,7 +16,7 @@ from . import _capi
 
 STAT_NAMES = ("n_in", "n_parents", "n_pairs", "n_orphans", "n_dropped", "n_out", "grid_cells", "cell_size",
               "max_radius", "ms_total", "ms_prep", "ms_grid", "ms_gate", "ms_sumlw", "ms_moments", "ms_compact", "ms_k_gate", "ms_k_moments", "n_certified_parents", "ms_host_enqueue",
-              "n_parents_local", "n_pairs_local", "shards")
+              "n_parents_local", "n_pairs_local", "shards", "tight_box")
 
 
 @dataclass
@@ -395,7 +395,7 @@ class HemContext:
         buf = (C.c_double * _capi.STEP_STATS_LEN)()
         self._check(self._lib.hem_step_stats(self._h, step, buf))
         d = dict(zip(STAT_NAMES, list(buf)))
-        for k in STAT_NAMES[:7] + STAT_NAMES[18:19] + STAT_NAMES[20:23]:
+        for k in STAT_NAMES[:7] + STAT_NAMES[18:19] + STAT_NAMES[20:24]:
             d[k] = int(d[k])
         return d
 

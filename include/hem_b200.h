@@ -61,6 +61,9 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *   "cell_scale"  grid cell = cell_scale * geometric-mean parent radius (default 0.55)
  *   "smd_prefilter" 1 (default) -> certified Mahalanobis pre-test inside the KLD gate (same
  *                 accepted sets, fewer full KLD evaluations); 0 evaluates every candidate in full
+ *   "tight_box"   1 (default) -> while the pre-test is on and no component of a level is uncertified, a certified parent
+ *                 searches the axis-aligned box of its Mahalanobis ellipsoid (intersected with its sphere's box): every
+ *                 candidate outside is one the pre-test rejects, so the accepted sets are unchanged; 0 -> sphere boxes
  *   "sumlw_mode"  0 (default) auto, 1 stable radix sort by child, 2 claim table: two bit-identical
  *                 ways of adding a child's claims in ascending parent order
  *   "overlap"     1 (default) -> stages of a step that do not depend on each other run side by side on a second stream
@@ -197,9 +200,10 @@ int hem_clear_outputs(hem_ctx* ctx);
  *   19 ms_host_enqueue (host wall time spent enqueueing the step, up to its closing sync)
  *   20 n_parents_local  21 n_pairs_local (this rank's share of the gate / moment work in a multi-GPU build;
  *      equal to 1 and 2 on one GPU)  22 shards (ranks the step was sharded over; 1 = built whole on every rank)
+ *   23 tight_box (1: certified parents searched the box of their Mahalanobis ellipsoid)
  * ms_* are CUDA-event times on the context's stream and are 0 unless the
  * "timing" option is set. */
-#define HEM_STEP_STATS_LEN 23
+#define HEM_STEP_STATS_LEN 24
 int hem_step_stats(const hem_ctx* ctx, int step, double* out);
 
 /* Cumulative counters of the context: "launches" (kernels of this library

@@ -669,7 +669,9 @@ def test_gpu_heavy_parent_moments_path(port):
         assert np.array_equal(a["is_parent"], d["is_parent"])
         for k in ("xyz", "colors", "opacity", "cov6", "sh", "weight"):
             assert group_relerr(a[k], d[k]) < 5e-4, k
-        assert group_relerr(d["weight"], r.level(1)["weight"]) < 1e-6      # the ordinary path follows the reference's order
+        # the ordinary path adds a parent's ~5900 terms one by one like the reference, in its own candidate order (the
+        # parent itself first, then grid order): the two FP32 sums agree to the drift of that length, inside the 1e-4 contract
+        assert group_relerr(d["weight"], r.level(1)["weight"]) < 1e-4
         err_heavy = np.abs(a["weight"] / w64 - 1.0).max()
         err_plain = np.abs(d["weight"] / w64 - 1.0).max()
         assert err_heavy <= err_plain and err_heavy < 2e-5, (err_heavy, err_plain)
