@@ -94,7 +94,7 @@ struct hem_ctx {
     bool box_valid = false;
     float box_lo[3] = { 0, 0, 0 }, box_hi[3] = { 0, 0, 0 };
     double box_q = 5e-4;
-    int64_t shard_min_n = 600000;  // multi-GPU: levels smaller than this are built redundantly on every rank
+    int64_t shard_min_n = 2000000; // multi-GPU: levels smaller than this are built redundantly on every rank (measured: a 1.1 M level loses to its exchanges at 2 ranks)
     uint32_t heavy_pairs = 16384;  // parents with more accepted pairs are accumulated by k_moments_heavy (0 = never)
     bool heavy_hint = false;       // a previous step met such a parent: launch k_moments_heavy from now on
     // the same for the gate, by rows of cells of the search box: a parent whose box has more rows than
@@ -121,7 +121,7 @@ struct hem_ctx {
     DevBuf radius, psafe, pflag, radius2, psafe2, pflag2;             // prep arrays, ping-pong by level parity
     DevBuf prank, key, key2, val, val2, sp0, sp1, sp2, sp3, cell_start;
     DevBuf ctlbuf, pair_off, pair_off_s, ptab, pinfo, csr_s, csr_pad, stage_geo, stage_sh, pool, chunks, csr_child, csr_wl, sk, sv, orank;
-    DevBuf valid, vflag, vpos, cubtmp, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done, seg_info, hv_hdr, seg_cnt, seg_off, seg_done;
+    DevBuf valid, vflag, vpos, cubtmp, tmp_geo, tmp_sh, claims, ovf, boxhist, heavy_part, heavy_done, seg_info, hv_hdr, seg_cnt, seg_off, seg_done, xstat;
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
@@ -131,6 +131,12 @@ struct hem_ctx {
     // control-block reset + parent-rank scan beside the grid build, orphan scan + copy beside the moment kernel
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // multi-GPU: the SH part of a sharded level's merged rows (180 of 244 bytes) is exchanged on its own stream while the
+    // next step builds its grid and runs its gates (they need geometry only); first reader: the next moment / orphan kernels
+    cudaStream_t xchg_stream = nullptr;
+    cudaEvent_t ev_xfork = nullptr, ev_shx = nullptr;
+    bool shx_pending = false;
+    DevBuf ptab2;                                // parent table of odd levels (the SH exchange of level l reads ptab while level l+1 writes its own)
     bool overlap = true;
     DevBuf cubtmp2;                              // CUB temp storage of the second stream
     // copy/compute overlap: SH rows arrive and finished levels leave on a second stream
@@ -246,7 +252,7 @@ template <class... KArgs> PdlLaunch<KArgs...> pdl(void (*kernel)(KArgs...), dim3
     return L;
 }
 
-int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk);
+int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk, cudaStream_t on = nullptr);
 
 // Multi-GPU build from HOST arrays: every rank uploads only its 1/world slice of the rows over its own
 // PCIe link and the ranks all-gather the slices over NVLink (the alternative — every rank uploading the
@@ -367,11 +373,11 @@ inline int64_t slab_chunk(int64_t np, int world) { return (np + world - 1) / wor
 inline int64_t slab_bound(int64_t np, int r, int world) { return std::min<int64_t>(slab_chunk(np, world) * r, np); }
 
 // in-place all-gather: rank r owns elements [r*chunk, (r+1)*chunk) of `buf` (G*chunk elements long)
-int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk)
+int allgather_equal(hem_ctx* ctx, void* buf, size_t elem, int64_t chunk, cudaStream_t on)
 {
     if (ctx->world <= 1 || chunk <= 0) return HEM_OK;
     const size_t bytes = (size_t)chunk * elem;
-    NK(g_nccl.AllGather((char*)buf + (size_t)ctx->rank * bytes, buf, bytes, /*ncclChar*/ 0, ctx->nccl_comm, ctx->stream));
+    NK(g_nccl.AllGather((char*)buf + (size_t)ctx->rank * bytes, buf, bytes, /*ncclChar*/ 0, ctx->nccl_comm, on ? on : ctx->stream));
     return HEM_OK;
 }
 
@@ -446,6 +452,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     StepStats& S = ctx->stats[l];
     const int64_t n = in.n;
     const int Fp = ctx->Fp;
+    DevBuf& PTAB = (l & 1) ? ctx->ptab2 : ctx->ptab;
     const float pp = 1.0f / hem_reduction;
     S = StepStats();
     S.n_in = n;
@@ -468,7 +475,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     //   [ Ctl | pair_cnt_s (n+1) | pair_cnt (n+1) | sumlw (n) | cnt_c (n) | heavy-parent list ]
     const size_t off_cnt_s = 256, off_cnt = off_cnt_s + ((size_t)(n + 1 + 64) * 4 + 255) / 256 * 256;   // +64: all-gather padding
     const size_t off_sumlw = off_cnt + ((size_t)(n + 1) * 4 + 255) / 256 * 256;
-    const size_t off_cntc = off_sumlw + ((size_t)n * 4 + 255) / 256 * 256;
+    const size_t off_cntc = off_sumlw + ((size_t)(n + 64) * 4 + 255) / 256 * 256;              // +64: all-gather padding
     const size_t off_heavy = off_cntc + ((size_t)n * 4 + 255) / 256 * 256;      // one byte per moment ticket
     const size_t ctl_bytes = (off_heavy + (size_t)(n / MOM_B + 2) + 15) / 16 * 16;
     CKR(ensure(ctx, ctx->ctlbuf, ctl_bytes));
@@ -553,6 +560,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     bool fork2 = false;
     auto orphan_stage = [&]() -> int {
         CKR(ensure(ctx, ctx->orank, n * 4));
+        if (ctx->shx_pending) {       // the SH rows of this level are still being exchanged: their first readers follow
+            CK(cudaStreamWaitEvent(st, ctx->ev_shx, 0));
+            if (ctx->aux_stream) CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_shx, 0));
+            ctx->shx_pending = false;
+        }
         fork2 = ctx->overlap && ctx->aux_stream && !(ctx->sh_pending && ctx->sh_gather_chunk > 0);
         cudaStream_t s2 = fork2 ? ctx->aux_stream : st;
         if (fork2) {
@@ -657,7 +669,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         S.n_parents_local = my_np; S.shards = G;
         CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
-        CKR(ensure(ctx, ctx->ptab, np * 8));
+        CKR(ensure(ctx, PTAB, np * 8));
         CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
         // ellipsoid boxes (k_ptab): only while the certified pre-test is active and every component can be pre-tested
         const float kthr_ = distance_delta * distance_delta * 0.5f;
@@ -666,7 +678,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         S.tight = s_box > 0.0f;
         pdl(k_ptab, blocks_for(np, 256), 256, 0, st)((uint32_t)(n - np), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                      ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, s_box, ctx->ptab.as<uint2>(),
+                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, s_box, PTAB.as<uint2>(),
                                                      ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
         size_t pool_cap = std::max<size_t>(std::max<size_t>(ctx->pool.cap / 8, ctx->pool_min), std::max<size_t>((size_t)8 * n / G, 1 << 16));
@@ -804,7 +816,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
                 pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for((int64_t)launch_chunks * 32, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
-                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), ctx->ptab.as<uint2>(), d_cnt_c,
+                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), PTAB.as<uint2>(), d_cnt_c,
                     fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P,
                     launched_gate_heavy ? ctx->seg_off.as<uint32_t>() : nullptr);
                 CK(cudaGetLastError()); ctx->n_launches++;
@@ -837,29 +849,44 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const bool need_canon = !use_claims || ctx->keep_pairs;
         if (need_canon) {
             if (G > 1) {    // sharded: counts arrive in cell order, put them in canonical order here
-                k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), d_pair_cnt_s, (int)np, d_pair_cnt);
+                k_cnt_canon<<<blocks_for(np, 256), 256, 0, st>>>(PTAB.as<uint2>(), d_pair_cnt_s, (int)np, d_pair_cnt);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
                 return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt, ctx->pair_off.as<uint32_t>(), (int)(np + 1), st);
             }));
             if (P > 0) {
-                k_csr_canon<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                k_csr_canon<<<blocks_for(np * 32, 256), 256, 0, st>>>(PTAB.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
                                                                        ctx->pair_off.as<uint32_t>(), ctx->csr_s.as<uint2>(), (int)np,
                                                                        ctx->csr_child.as<uint32_t>(), ctx->csr_wl.as<float>());
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
         }
         if (P > 0 && use_claims) {
+            // sharded step: every rank holds all pairs, but files and sums the claims of its own range of children only
+            // (1/G of the atomics and of the table traffic); the G slices of sumLw are then all-gathered (4 bytes per child)
+            const int64_t cchunk = (n + G - 1) / G;
+            const int64_t c_lo = G > 1 ? std::min<int64_t>(cchunk * R, n) : 0, c_hi = G > 1 ? std::min<int64_t>(c_lo + cchunk, n) : n;
             if (!fuse_claims) {
-                pdl(k_claims, blocks_for(np * 32, 256), 256, 0, st)(ctx->ptab.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
+                pdl(k_claims, blocks_for(np * 32, 256), 256, 0, st)(PTAB.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
                                                                     ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
-                                                                    ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters);
+                                                                    ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters,
+                                                                    (uint32_t)c_lo, (uint32_t)c_hi);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
-            pdl(k_sumlw_claims, blocks_for(n, 256), 256, 0, st)(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
-                                                                ctx->sumlw_mode == 2 ? ~0ull : 4096ull, n, d_sumlw);
-            CK(cudaGetLastError()); ctx->n_launches++;
+            if (c_hi > c_lo) {
+                pdl(k_sumlw_claims, blocks_for(c_hi - c_lo, 256), 256, 0, st)(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
+                                                                              ctx->sumlw_mode == 2 ? ~0ull : 4096ull, c_lo, c_hi, d_sumlw);
+                CK(cudaGetLastError()); ctx->n_launches++;
+            }
+            if (G > 1) {
+                CKR(allgather_equal(ctx, d_sumlw, 4, cchunk));
+                CKR(ensure(ctx, ctx->xstat, 64 * 8));
+                k_status_put<<<1, 1, 0, st>>>(d_counters, ctx->xstat.as<unsigned long long>(), R);
+                CKR(allgather_equal(ctx, ctx->xstat.p, 8, 1));
+                k_status_or<<<1, 1, 0, st>>>(d_counters, ctx->xstat.as<unsigned long long>(), G);
+                CK(cudaGetLastError()); ctx->n_launches += 2;
+            }
         } else if (P > 0) {
             CKR(ensure(ctx, ctx->sk, P * 4));
             CKR(ensure(ctx, ctx->sv, P * 4));
@@ -877,7 +904,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         // ---- S4 moments -------------------------------------------------------------------------------
         nvtx.next("S4 moments");
         MomArgs M;
-        M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = ctx->ptab.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
+        M.geo = geo; M.sh = sh; M.Fp = Fp; M.ptab = PTAB.as<uint2>(); M.pair_off_s = ctx->pair_off_s.as<uint32_t>();
         M.csr_s = ctx->csr_s.as<uint2>(); M.sumlw = d_sumlw;
         M.t_begin = (int)tb[R]; M.t_end = (int)tb[R + 1];
         M.counters = d_counters;
@@ -934,12 +961,26 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (G > 1) {
             // all-gather the merged rows (staged in cell order, one contiguous range per rank), then put
             // them at their canonical place: every rank ends the step with the complete next level
+            // geometry rows first (what the next step's prep, grid and gates read) ...
             CKR(allgather_equal(ctx, ctx->stage_geo.p, 64, slab_chunk(np, G)));
-            if (Fp > 0) CKR(allgather_equal(ctx, ctx->stage_sh.p, (size_t)Fp * 4, slab_chunk(np, G)));
-            k_permute_rows<<<blocks_for(np * 32, 256), 256, 0, st>>>(ctx->ptab.as<uint2>(), (int)np, ctx->stage_geo.as<float4>(),
+            k_permute_rows<<<blocks_for(np * 32, 256), 256, 0, st>>>(PTAB.as<uint2>(), (int)np, ctx->stage_geo.as<float4>(),
                                                                       ctx->stage_sh.as<float>(), Fp, out.geo.as<float4>(),
-                                                                      out.sh.as<float>());
+                                                                      out.sh.as<float>(), 1, 0);
             CK(cudaGetLastError()); ctx->n_launches++;
+            // ... the SH rows on the exchange stream, beside whatever follows on the main stream
+            if (Fp > 0) {
+                cudaStream_t xs = (ctx->overlap && ctx->xchg_stream) ? ctx->xchg_stream : st;
+                if (xs != st) {
+                    CK(cudaEventRecord(ctx->ev_xfork, st));
+                    CK(cudaStreamWaitEvent(xs, ctx->ev_xfork, 0));
+                }
+                CKR(allgather_equal(ctx, ctx->stage_sh.p, (size_t)Fp * 4, slab_chunk(np, G), xs));
+                k_permute_rows<<<blocks_for(np * 32, 256), 256, 0, xs>>>(PTAB.as<uint2>(), (int)np, ctx->stage_geo.as<float4>(),
+                                                                          ctx->stage_sh.as<float>(), Fp, out.geo.as<float4>(),
+                                                                          out.sh.as<float>(), 0, 1);
+                CK(cudaGetLastError()); ctx->n_launches++;
+                if (xs != st) { CK(cudaEventRecord(ctx->ev_shx, xs)); ctx->shx_pending = true; }
+            }
         }
     } else {
         CKR(join1());
@@ -1186,6 +1227,9 @@ hem_ctx* hem_create(int device, uint64_t seed)
     ctx->stream = ctx->own_stream;
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->xchg_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_xfork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_shx, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* cs = getenv("HEM_OVERLAP")) ctx->overlap = atoi(cs) != 0;
@@ -1210,9 +1254,9 @@ void hem_destroy(hem_ctx* ctx)
                       &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->out_d, &ctx->out_e, &ctx->out_f, &ctx->out_g,
                       &ctx->radius, &ctx->psafe, &ctx->pflag, &ctx->radius2, &ctx->psafe2, &ctx->pflag2, &ctx->prank, &ctx->key, &ctx->key2, &ctx->val, &ctx->val2,
                       &ctx->sp0, &ctx->sp1, &ctx->sp2, &ctx->sp3, &ctx->cell_start,
-                      &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
+                      &ctx->ctlbuf, &ctx->pair_off, &ctx->pair_off_s, &ctx->ptab, &ctx->ptab2, &ctx->pinfo, &ctx->csr_s, &ctx->csr_pad, &ctx->stage_geo, &ctx->stage_sh, &ctx->pool, &ctx->chunks, &ctx->csr_child,
                       &ctx->csr_wl, &ctx->sk, &ctx->sv, &ctx->orank, &ctx->valid, &ctx->vflag,
-                      &ctx->vpos, &ctx->cubtmp, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done, &ctx->seg_info, &ctx->hv_hdr,
+                      &ctx->vpos, &ctx->cubtmp, &ctx->tmp_geo, &ctx->tmp_sh, &ctx->claims, &ctx->ovf, &ctx->boxhist, &ctx->heavy_part, &ctx->heavy_done, &ctx->seg_info, &ctx->hv_hdr, &ctx->xstat,
                       &ctx->seg_cnt, &ctx->seg_off, &ctx->seg_done,
                       &ctx->icp_src, &ctx->icp_tgt, &ctx->icp_box, &ctx->icp_key, &ctx->icp_key2, &ctx->icp_val, &ctx->icp_val2,
                       &ctx->icp_rows, &ctx->icp_start, &ctx->icp_part, &ctx->icp_state, &ctx->icp_corr };
@@ -1224,6 +1268,9 @@ void hem_destroy(hem_ctx* ctx)
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->xchg_stream) { cudaStreamSynchronize(ctx->xchg_stream); cudaStreamDestroy(ctx->xchg_stream); }
+    for (cudaEvent_t e : { ctx->ev_xfork, ctx->ev_shx }) if (e) cudaEventDestroy(e);
+    release(ctx->ptab2);
     for (cudaEvent_t e : { ctx->ev_fork, ctx->ev_join }) if (e) cudaEventDestroy(e);
     release(ctx->cubtmp2);
     for (cudaEvent_t e : { ctx->ev_geo, ctx->ev_sh, ctx->ev_level }) if (e) cudaEventDestroy(e);
@@ -1286,6 +1333,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
 
     ctx->prep_valid = false;
     ctx->box_valid = false;
+    if (ctx->shx_pending) { cudaStreamSynchronize(ctx->xchg_stream); ctx->shx_pending = false; }
     ctx->sh_pending = false;       // a build that failed half-way must not leave a stale wait / all-gather behind
     ctx->sh_gather_chunk = 0;
     // level 0 = the input (Mixture::initMixture, mixture.cpp:287-333)
@@ -1372,6 +1420,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
                 }
                 CK(cudaEventRecord(ctx->ev_level, st));
                 CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_level, 0));
+                if (ctx->shx_pending) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_shx, 0));      // SH rows still in the exchange
                 cudaStream_t cs = ctx->copy_stream;
                 if (B.sh && ctx->F > 0) {
                     const bool to_dev = is_device_ptr(B.sh);
@@ -1386,6 +1435,7 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
         }
     }
     if (ctx->sh_pending) CKR(wait_sh(ctx));
+    if (ctx->shx_pending) { CK(cudaStreamSynchronize(ctx->xchg_stream)); ctx->shx_pending = false; }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }

@@ -1022,7 +1022,8 @@ __global__ void k_csr_canon(const uint2* __restrict__ ptab, const uint32_t* __re
 __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
                          const uint2* __restrict__ csr_s, int np, uint32_t* __restrict__ cnt_c,
                          uint2* __restrict__ claims, uint4* __restrict__ ovf, unsigned long long ovf_cap,
-                         unsigned long long pool_cap, unsigned long long* __restrict__ counters)
+                         unsigned long long pool_cap, unsigned long long* __restrict__ counters,
+                         uint32_t c_lo, uint32_t c_hi)      // only children in [c_lo, c_hi): this rank's share of the normaliser
 {
     pdl_enter();
     if (pool_overflowed(counters, pool_cap)) return;
@@ -1033,6 +1034,7 @@ __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restr
     const uint32_t srank = ptab[t].y;
     for (uint32_t k = a + lane; k < e; k += 32) {
         const uint2 p = csr_s[k];
+        if (p.x < c_lo || p.x >= c_hi) continue;
         const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
         if (slot < (uint32_t)CLAIM_K) {
             claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
@@ -1043,12 +1045,24 @@ __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restr
     }
 }
 
+// multi-GPU: the ranks agree on "the claim table gave up" (each rank sums its own range of children)
+__global__ void k_status_put(const unsigned long long* __restrict__ counters, unsigned long long* __restrict__ slots, int rank)
+{
+    slots[rank] = counters[C_FAIL];
+}
+__global__ void k_status_or(unsigned long long* __restrict__ counters, const unsigned long long* __restrict__ slots, int world)
+{
+    unsigned long long v = 0ull;
+    for (int r = 0; r < world; ++r) v |= slots[r];
+    counters[C_FAIL] = v;
+}
+
 __global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ claims,
                                const uint4* __restrict__ ovf, unsigned long long* __restrict__ counters,
-                               unsigned long long ovf_limit, int64_t n, float* __restrict__ sumlw)
+                               unsigned long long ovf_limit, int64_t c_lo, int64_t n, float* __restrict__ sumlw)
 {
     pdl_enter();
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c = c_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // children [c_lo, n)
     if (c >= n) return;
     const uint32_t m = cnt_c[c];
     if (m == 0) return;                                  // orphan: sumLw stays exactly 0
@@ -1549,14 +1563,15 @@ k_finish(float4* __restrict__ geo, int64_t np, const uint32_t* __restrict__ oran
 // staged merged rows (index = cell-order position t) -> their final place (index = canonical rank)
 __global__ void k_permute_rows(const uint2* __restrict__ ptab, int np, const float4* __restrict__ sgeo,
                                const float* __restrict__ ssh, int Fp, float4* __restrict__ ogeo,
-                               float* __restrict__ osh)
+                               float* __restrict__ osh, int do_geo, int do_sh)
 {
     const int lane = threadIdx.x & 31;
     const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= np) return;
     const size_t d = ptab[t].y;
-    if (lane < 4) ogeo[4 * d + lane] = sgeo[4 * (size_t)t + lane];
-    for (int q = lane; q < Fp; q += 32) osh[d * Fp + q] = ssh[(size_t)t * Fp + q];
+    if (do_geo && lane < 4) ogeo[4 * d + lane] = sgeo[4 * (size_t)t + lane];
+    if (do_sh)
+        for (int q = lane; q < Fp; q += 32) osh[d * Fp + q] = ssh[(size_t)t * Fp + q];
 }
 
 __global__ void k_valid_flag(const uint8_t* __restrict__ valid, int64_t n, uint32_t* __restrict__ out)

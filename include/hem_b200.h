@@ -73,7 +73,7 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 parent of geometric-mean radius) is scanned by the whole grid in segments instead of by one warp
  *                 (defaults 128 and 16; heavy_rows = 0: never; single GPU)
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
- *                 being sharded (default 600000; the per-level exchanges cost more than they save below it)
+ *                 being sharded (default 2000000; the per-level exchanges cost more than they save below it)
  *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own
  *                 PCIe link and the slices are all-gathered over NVLink; 0 -> every rank uploads everything
  *   "heavy_pairs" parents with more accepted pairs than this are accumulated by the grid-wide split kernel
