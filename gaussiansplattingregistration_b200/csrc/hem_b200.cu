@@ -707,6 +707,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             A.kthr = distance_delta * distance_delta * 0.5f;     // mixture.cpp:128
             A.decay2 = decay_rate * decay_rate;                  // mixture.cpp:58,61
             A.smd_rej = (ctx->smd_prefilter && A.kthr <= 1e4f) ? 2.0f * A.kthr + 0.5f : INFINITY;
+            A.all_cert = ps.n_uncert == 0 ? 1 : 0;
             A.pair_cnt_s = d_pair_cnt_s;
             A.pair_cnt = (G == 1) ? d_pair_cnt : nullptr;      // used only by the canonical-CSR (sort / white-box) path
             A.pool = ctx->pool.as<uint2>(); A.pool_cap = pool_cap;

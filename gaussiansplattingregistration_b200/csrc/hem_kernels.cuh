@@ -550,6 +550,7 @@ struct GateArgs {
     int tb;                      // parents per work ticket (1..GATE_TB)
     float cthr, kthr, decay2;
     float smd_rej;               // smd pre-test threshold 2*kthr + 0.5 (+inf disables it)
+    int all_cert;                // no component of the level is uncertified: candidates need no certificate lookup
     uint32_t* pair_cnt_s;        // [np+1] accepted pairs of the parent at cell-order position t
     uint32_t* pair_cnt;          // [np+1] same, indexed by canonical rank (single GPU; NULL when sharded)
     uint2* pool; unsigned long long pool_cap;
@@ -749,17 +750,22 @@ k_gate(GateArgs A)
             float smd = 0.0f;
             if (lane < m) {
                 jj = q[lane];
-                const float4 c1 = A.sp1[jj], c0 = A.sp0[jj];
-                const uint32_t ccert = __float_as_uint(A.sp3[jj].w);
-                // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
-                const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
-                if (!(cdist > A.cthr)) {
-                    const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
-                    const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
-                    const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
-                    const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
-                    smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
-                    keep = !(pcert && ccert != 0u && smd > A.smd_rej);
+                const float4 c0 = A.sp0[jj];
+                // Both gates must pass, so their order is free: the Mahalanobis pre-test goes first (it rejects more than
+                // half of what reaches this stage and needs nothing but the mean), the colour row is fetched for the rest.
+                const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
+                const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
+                const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
+                const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
+                smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
+                bool rej = false;
+                if (pcert && smd > A.smd_rej)          // certified pre-test (hem_math.cuh): needs a certified candidate as well
+                    rej = A.all_cert || __float_as_uint(A.sp3[jj].w) != 0u;
+                if (!rej) {
+                    // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
+                    const float4 c1 = A.sp1[jj];
+                    const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
+                    keep = !(cdist > A.cthr);
                 }
             }
             const unsigned km = __ballot_sync(full, keep);

@@ -17,6 +17,16 @@ d = synth(6000, seed=7, density=200000.0)
 ctx2 = HemContext(0, 7)
 ctx2.build(*d.arrays(), cluster_level=2)
 print("dense sizes", [ctx2.level_size(l) for l in range(3)], ctx2.step_stats(0)["n_pairs"])
+# round 2: heavy-parent gate split (row threshold forced down), from_mixture, overlap off
+ctx3 = HemContext(0, 7)
+ctx3.set_option("heavy_rows", 32); ctx3.set_option("heavy_rows_rel", 0)
+ctx3.build(*g.arrays(), cluster_level=2)
+ctx3.build(*g.arrays(), cluster_level=2)
+m = ctx3.from_mixture(1)
+print("heavy gate sizes", [ctx3.level_size(l) for l in range(3)], float(m["_rotation"].float().nan_to_num().sum()))
+ctx3.set_option("overlap", 0)
+ctx3.build(*c.arrays(), cluster_level=2)
+print("no-overlap sizes", [ctx3.level_size(l) for l in range(3)])
 # ICP consumer: two small pyramids, coarse-to-fine; plus host arrays with correspondences and a fringe (no match) part
 from gaussiansplattingregistration_b200.synth import rigid_copy
 a = synth(20000, seed=8, density=5000.0)

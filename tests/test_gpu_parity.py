@@ -555,6 +555,15 @@ def test_gpu_plane_inlier_merging_matches_oracle(port):
             assert_level_close(got[d], want, what=f"plane merging level {d}")
         else:
             assert abs(got[d]["xyz"].shape[0] - want["xyz"].shape[0]) <= 4
+    # planes side by side on several contexts (the default) == one after the other on one context, bit for bit
+    from gaussiansplattingregistration_b200.hem import HemContext
+    many = [np.sort(perm[k * 1500:(k + 1) * 1500]) for k in range(9)]
+    with HemContext(0, seed=21) as one:
+        seq = merge_plane_inliers(*c.arrays(), many, p, ctx=one)
+    par = merge_plane_inliers(*c.arrays(), many, p, seed=21, concurrency=4)
+    for d in range(2):
+        for k in seq[d]:
+            assert np.array_equal(seq[d][k], par[d][k]), (d, k)
 
 
 def test_gpu_random_sweep_vs_oracle(port):
