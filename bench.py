@@ -432,7 +432,8 @@ def run_b200_arm(a, rank, local_rank, world):
         import csv
         rows = {r[0]: r for r in csv.reader(open(prof)) if r}
         try:
-            traffic = (float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])) * 1e6
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = sum(float(rows[m][2]) * unit[rows[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             s0 = stats[0]
             traffic_note = (f"ncu --set full, level-0 k_gate launch on one GPU ({os.path.basename(prof)}); algorithmic bytes "
                             f"of that launch = {(64 * s0['n_in'] + 60 * s0['n_parents'] + 12 * s0['n_pairs']) / 1e6:.1f} MB")

@@ -1234,6 +1234,8 @@ hem_ctx* hem_create(int device, uint64_t seed)
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* cs = getenv("HEM_OVERLAP")) ctx->overlap = atoi(cs) != 0;
+    if (const char* cs = getenv("HEM_HEAVY_ROWS")) ctx->heavy_rows = atoi(cs);
+    if (const char* cs = getenv("HEM_HEAVY_REL")) ctx->heavy_rows_rel = atof(cs);
     cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_sh, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_level, cudaEventDisableTiming);

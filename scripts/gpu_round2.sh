@@ -7,3 +7,6 @@ timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_ou
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.json | cut -c1-600
+bash scripts/gpu_prof.sh 3m
+timeout 900 bash scripts/gpu_sanitize.sh 2>&1 | tee gpurun_out/sanitize.log | tail -30
+timeout 600 python bench.py --workload 10m --steps 5 --warmup 3 --skip-e2e --no-cpu-baseline --no-extra 2>&1 | tail -1 | tee gpurun_out/bench10m_n1.json | cut -c1-200

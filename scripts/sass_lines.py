@@ -1,5 +1,5 @@
 """Attribute an ncu SASS source page to CUDA source lines (the CLI's CUDA view carries no metrics).
-usage: python scripts/sass_lines.py <report.ncu-rep> <kernel regex> <lib.so> [top N]
+usage: python scripts/sass_lines.py <report.ncu-rep> <kernel regex (mangled name in the cubin)> <lib.so> [top N] [ncu kernel-name regex]
 Needs the library the report was captured from (built with -lineinfo)."""
 import csv
 import os
@@ -10,6 +10,7 @@ import tempfile
 
 rep, kern, lib = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+kern_ncu = sys.argv[5] if len(sys.argv) > 5 else kern
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -32,7 +33,7 @@ for l in dis.splitlines():
 name = [f for f in funcs if re.search(kern, f)]
 assert name, list(funcs)[:20]
 ins = funcs[name[0]]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern_ncu], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
 h = rows[hi]
