@@ -59,6 +59,7 @@ struct StepStats {
     int64_t n_parents_local = 0, n_pairs_local = 0;   // this rank's share of the gate / moment work (multi-GPU)
     int shards = 1;                                   // ranks the step was sharded over
     bool tight = false;                               // ellipsoid boxes were used
+    bool timed = false, timed_pairs = false;          // events of this step were recorded (read at the end of the build)
     double cell_size = 0, max_radius = 0;
     double ms_host = 0;       // host time spent enqueueing the step (up to its closing sync)
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
@@ -125,7 +126,9 @@ struct hem_ctx {
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
-    cudaEvent_t ev[EV_COUNT] = {};
+    // timing events, one set per level: recorded while the steps run, read once at the end of the build (a readout per
+    // step cost an extra event synchronisation per level)
+    std::vector<std::vector<cudaEvent_t>> evs;
 
     // independent stages of a step run beside the main chain on a second stream (fork / join by events):
     // control-block reset + parent-rank scan beside the grid build, orphan scan + copy beside the moment kernel
@@ -457,12 +460,21 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     S = StepStats();
     S.n_in = n;
     const auto host_t0 = std::chrono::steady_clock::now();
+    cudaEvent_t* ev = nullptr;
+    if (ctx->timing) {
+        if (ctx->evs.size() <= (size_t)l) ctx->evs.resize((size_t)l + 1);
+        if (ctx->evs[l].empty()) {
+            ctx->evs[l].assign(EV_COUNT, nullptr);
+            for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&ctx->evs[l][i]));
+        }
+        ev = ctx->evs[l].data();
+    }
     char nvtx_name[48];
     snprintf(nvtx_name, sizeof nvtx_name, "hem.step level %d (n=%lld)", l, (long long)in.n);
     NvtxRange nvtx_step(nvtx_name);
     NvtxMark nvtx;
     nvtx.next("S1 prep");
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_BEGIN], st));
+    if (ctx->timing) CK(cudaEventRecord(ev[EV_BEGIN], st));
 
     if (n == 0) { out.n = 0; return HEM_OK; }
     if (n >= (int64_t)1 << 31) { ctx->err = "more than 2^31-1 components per level is not supported"; return HEM_ERR_INVALID; }
@@ -539,7 +551,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     float max_radius = 0.0f;
     memcpy(&max_radius, &ps.max_radius_bits, 4);
     S.max_radius = max_radius;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_PREP], st));
+    if (ctx->timing) CK(cudaEventRecord(ev[EV_PREP], st));
 
     // next level store: upper bound n + np rows (a NaN-radius parent is both a merged row and an orphan)
     const int64_t cap_rows = n + np;
@@ -656,7 +668,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                              ctx->cell_start.as<uint32_t>());
         CK(cudaGetLastError()); ctx->n_launches++;
         CKR(join1());
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GRID], st));
+        if (ctx->timing) CK(cudaEventRecord(ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
         nvtx.next("S3 gate");
@@ -742,7 +754,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 A.seg_info = ctx->seg_info.as<uint4>();
                 A.hv_hdr = ctx->hv_hdr.as<uint32_t>();
             }
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK0], st));
+            if (ctx->timing) CK(cudaEventRecord(ev[EV_GK0], st));
             if (my_np > 0) {
                 // ticket size: GATE_TB parents amortise the ticket/pool atomics on big levels; on small levels
                 // (fewer parents than a few per resident warp) one parent per ticket keeps every warp busy and
@@ -759,7 +771,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 CK(cudaGetLastError());
                 ctx->n_launches++;
             }
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GK1], st));
+            if (ctx->timing) CK(cudaEventRecord(ev[EV_GK1], st));
             if (G == 1) {       // single GPU: counts are complete, scan before the one host sync of this stage
                 CKR(cub_call(ctx, [&](void* tt, size_t& bb) {
                     return cub::DeviceScan::ExclusiveSum(tt, bb, d_pair_cnt_s, ctx->pair_off_s.as<uint32_t>(),
@@ -814,8 +826,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         }
         if (G == 1) {
             if (fast || nchunks > 0) {
-                const unsigned long long launch_chunks = fast ? (unsigned long long)chunk_cap_used : nchunks;
-                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for((int64_t)launch_chunks * 32, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
+                const int64_t launch_pairs = fast ? (int64_t)pool_cap : P;          // one lane per pool entry
+                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for(launch_pairs, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), PTAB.as<uint2>(), d_cnt_c,
                     fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P,
@@ -829,7 +841,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             for (int q = 0; q < G; ++q) M = std::max(M, pb[q + 1] - pb[q]);
             CKR(ensure(ctx, ctx->csr_pad, (size_t)std::max<int64_t>(M, 1) * G * 8));
             if (nchunks > 0) {
-                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for((int64_t)nchunks * 32, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
+                pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for(pb[R + 1] - pb[R], 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>(),
                     nullptr, nullptr, nullptr, nullptr, 0ull, nullptr);
@@ -841,7 +853,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                     CK(cudaMemcpyAsync(ctx->csr_s.as<uint2>() + pb[q], ctx->csr_pad.as<uint2>() + (size_t)q * M,
                                        (size_t)(pb[q + 1] - pb[q]) * 8, cudaMemcpyDeviceToDevice, st));
         }
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_GATE], st));
+        if (ctx->timing) CK(cudaEventRecord(ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
         nvtx.next("S3 sumLw");
@@ -899,7 +911,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         }
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+        if (ctx->timing) CK(cudaEventRecord(ev[EV_SUMLW], st));
         CKR(orphan_stage());
 
         // ---- S4 moments -------------------------------------------------------------------------------
@@ -922,7 +934,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
         if (ctx->sh_pending) CKR(wait_sh(ctx));
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK0], st));
+        if (ctx->timing) CK(cudaEventRecord(ev[EV_MK0], st));
         if (my_np > 0) {
             const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
             // Parents above heavy_pairs pairs are split over the whole grid (k_moments_heavy).  An ordinary cloud has
@@ -958,7 +970,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CK(cudaGetLastError());
             ctx->n_launches++;
         }
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MK1], st));
+        if (ctx->timing) CK(cudaEventRecord(ev[EV_MK1], st));
         if (G > 1) {
             // all-gather the merged rows (staged in cell order, one contiguous range per rank), then put
             // them at their canonical place: every rank ends the step with the complete next level
@@ -986,13 +998,13 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     } else {
         CKR(join1());
         if (ctx->timing) {
-            CK(cudaEventRecord(ctx->ev[EV_GRID], st));
-            CK(cudaEventRecord(ctx->ev[EV_GATE], st));
-            CK(cudaEventRecord(ctx->ev[EV_SUMLW], st));
+            CK(cudaEventRecord(ev[EV_GRID], st));
+            CK(cudaEventRecord(ev[EV_GATE], st));
+            CK(cudaEventRecord(ev[EV_SUMLW], st));
         }
         CKR(orphan_stage());
     }
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[EV_MOM], st));
+    if (ctx->timing) CK(cudaEventRecord(ev[EV_MOM], st));
 
     // ---- S5 filter ---------------------------------------------------------------------------------------
     nvtx.next("S5 finish");
@@ -1006,6 +1018,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CK(cudaGetLastError()); ctx->n_launches++;
     pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
     CK(cudaGetLastError());
+    if (ctx->timing) CK(cudaEventRecord(ev[EV_END], st));
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     CK(cudaStreamSynchronize(st));                                      // sync C
     memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
@@ -1092,22 +1105,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         nx.max_radius_bits = hc.nx_max_radius_bits; nx.n_radius = hc.nx_n_radius; nx.n_parents = hc.nx_n_parents;
         nx.n_certified = hc.nx_n_certified; nx.sum_radius_fx = hc.nx_sum_radius_fx; nx.n_uncert = hc.nx_n_uncert;
     }
-    if (ctx->timing) {
-        CK(cudaEventRecord(ctx->ev[EV_END], st));
-        CK(cudaEventSynchronize(ctx->ev[EV_END]));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_BEGIN], ctx->ev[EV_END]); S.ms[0] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_BEGIN], ctx->ev[EV_PREP]); S.ms[1] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_PREP], ctx->ev[EV_GRID]); S.ms[2] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_GRID], ctx->ev[EV_GATE]); S.ms[3] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_GATE], ctx->ev[EV_SUMLW]); S.ms[4] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_SUMLW], ctx->ev[EV_MOM]); S.ms[5] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[EV_MOM], ctx->ev[EV_END]); S.ms[6] = ms;
-        if (have_pairs) {
-            cudaEventElapsedTime(&ms, ctx->ev[EV_GK0], ctx->ev[EV_GK1]); S.ms[7] = ms;
-            cudaEventElapsedTime(&ms, ctx->ev[EV_MK0], ctx->ev[EV_MK1]); S.ms[8] = ms;
-        }
-    }
+    S.timed = ctx->timing; S.timed_pairs = have_pairs;
 
     if (ctx->keep_pairs) {
         StepPairs& K = ctx->pairs[l];
@@ -1243,7 +1241,6 @@ hem_ctx* hem_create(int device, uint64_t seed)
     if (const char* cs = getenv("HEM_GATE_TICKET")) g_gate_tb = atoi(cs);
     if (const char* cs = getenv("HEM_CELL_OCC")) { double v = atof(cs); if (v >= 0) ctx->cell_occupancy = v; }
     if (const char* cs = getenv("HEM_CELL_SCALE")) { double v = atof(cs); if (v > 0) ctx->cell_scale = v; }
-    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
 }
 
@@ -1268,7 +1265,7 @@ void hem_destroy(hem_ctx* ctx)
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_icp) cudaFreeHost(ctx->h_icp);
     for (cudaEvent_t e : { ctx->ev_icp0, ctx->ev_icp1 }) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& set : ctx->evs) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->xchg_stream) { cudaStreamSynchronize(ctx->xchg_stream); cudaStreamDestroy(ctx->xchg_stream); }
@@ -1441,6 +1438,20 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     if (ctx->shx_pending) { CK(cudaStreamSynchronize(ctx->xchg_stream)); ctx->shx_pending = false; }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    for (uint32_t l = 0; l < cluster_level && l < ctx->evs.size(); ++l) {      // stage times of every step, read once
+        StepStats& S = ctx->stats[l];
+        if (!S.timed || ctx->evs[l].empty() || S.n_in == 0) continue;
+        cudaEvent_t* ev = ctx->evs[l].data();
+        float ms = 0;
+        const int pairs[7][2] = { { EV_BEGIN, EV_END }, { EV_BEGIN, EV_PREP }, { EV_PREP, EV_GRID }, { EV_GRID, EV_GATE },
+                                  { EV_GATE, EV_SUMLW }, { EV_SUMLW, EV_MOM }, { EV_MOM, EV_END } };
+        for (int k = 0; k < 7; ++k)
+            if (cudaEventElapsedTime(&ms, ev[pairs[k][0]], ev[pairs[k][1]]) == cudaSuccess) S.ms[k] = ms; else cudaGetLastError();
+        if (S.timed_pairs) {
+            if (cudaEventElapsedTime(&ms, ev[EV_GK0], ev[EV_GK1]) == cudaSuccess) S.ms[7] = ms; else cudaGetLastError();
+            if (cudaEventElapsedTime(&ms, ev[EV_MK0], ev[EV_MK1]) == cudaSuccess) S.ms[8] = ms; else cudaGetLastError();
+        }
+    }
     if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }
     return HEM_OK;
 }

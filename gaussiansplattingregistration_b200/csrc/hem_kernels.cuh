@@ -962,29 +962,46 @@ __global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long lon
 {
     pdl_enter();
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    // the number of chunks written is read on the device; the grid is sized by the host's upper bound and capped, warps
-    // stride over the chunks (a launch over the whole capacity spent most of its time on warps with nothing to do)
-    const unsigned long long nchunks = min(counters[C_POOL] >> POOL_BITS, chunk_cap);
+    // One lane per POOL ENTRY (a warp per chunk ran at a quarter of its lanes: a chunk holds ~8 pairs).  Chunk ids and pool
+    // offsets come from the same packed atomic, so the chunk records are sorted by pool offset: a warp finds the chunk of its
+    // first entry by bisection, the chunks that start inside its 32-entry window mark their start lanes, and every lane counts
+    // the marks up to itself.  The counts are read on the device; the launch is sized by the host's upper bound and capped.
+    const unsigned long long packed = counters[C_POOL];
+    const uint32_t nchunks = (uint32_t)min(packed >> POOL_BITS, chunk_cap);
+    const unsigned long long npairs = packed & ((1ull << POOL_BITS) - 1ull);
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nchunks; c += nwarps) {
-        uint4 ch = chunks[c];
+    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32ull < npairs; w += nwarps) {
+        const uint32_t e0 = (uint32_t)(w * 32ull);
+        uint32_t lo = 0, hi = nchunks;                      // chunks[lo].y <= e0 < chunks[hi].y
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (chunks[mid].y <= e0) lo = mid; else hi = mid;
+        }
+        uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+        if (lo + (uint32_t)lane < nchunks) mine = chunks[lo + lane];
+        const bool inwin = lane > 0 && lo + (uint32_t)lane < nchunks && mine.y - e0 < 32u;      // starts inside the window (lane 0 = the chunk of e0)
+        const unsigned marks = __reduce_or_sync(full, inwin ? (1u << (mine.y - e0)) : 0u);
+        const int src = __popc(marks & ((2u << lane) - 1u));            // chunk of entry e0 + lane, relative to lo (< 32: each chunk has >= 1 pair)
+        uint4 ch;
+        ch.x = __shfl_sync(full, mine.x, src); ch.y = __shfl_sync(full, mine.y, src);
+        ch.z = __shfl_sync(full, mine.z, src); ch.w = __shfl_sync(full, mine.w, src);
+        const unsigned long long e = (unsigned long long)e0 + lane;
+        if (e >= npairs) continue;
         // a chunk of a heavy parent's segment carries the segment (index + 1) above the count: its prefix is relative to the segment
         if (ch.z >> 8) ch.w += seg_off[(ch.z >> 8) - 1u];
-        ch.z &= 0xffu;
-        const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w;    // dst_shift: offset into a rank's padded segment
-        const uint32_t srank = claims ? ptab[ch.x].y : 0u;
-        for (uint32_t k = lane; k < ch.z; k += 32) {
-            const uint2 p = pool[(size_t)ch.y + k];
-            csr_s[dst + k] = p;
-            if (claims) {
-                const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
-                if (slot < (uint32_t)CLAIM_K) {
-                    claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
-                } else {
-                    const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
-                    if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
-                }
+        const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w + (size_t)(e - ch.y);    // dst_shift: offset into a rank's padded segment
+        const uint2 p = pool[e];
+        csr_s[dst] = p;
+        if (claims) {
+            const uint32_t srank = ptab[ch.x].y;
+            const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
+            if (slot < (uint32_t)CLAIM_K) {
+                claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
+            } else {
+                const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+                if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
             }
         }
     }
