@@ -787,3 +787,32 @@ def test_gpu_torch_tensor_argument_checks():
         s.synchronize()
         for k in ("xyz", "cov6", "sh"):
             assert np.array_equal(got[k].cpu().numpy(), want[k], equal_nan=True), k
+
+
+def test_gpu_round2_switches_do_not_change_results():
+    """Ellipsoid boxes (`tight_box`), the two-stream overlap (`overlap`) and the heavy-gate split (`heavy_rows`) are pure
+    scheduling / culling choices: every level of a 300 k-splat, 3-level pyramid is bit-identical with each of them on or
+    off, pairs included (the boxes may only drop candidates the certified pre-test rejects)."""
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(300_000, seed=77, density=5000.0)
+    ref_levels = ref_pairs = None
+    for opts in ({}, {"tight_box": 0}, {"overlap": 0}, {"tight_box": 0, "overlap": 0}, {"heavy_rows": 48, "heavy_rows_rel": 0}):
+        with HemContext(0, seed=13) as ctx:
+            ctx.set_option("keep_pairs", 1)
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            ctx.build(*c.arrays(), cluster_level=3)
+            if "heavy_rows" in opts:
+                ctx.build(*c.arrays(), cluster_level=3)        # the first build reports the heavy parents, this one splits them
+            levels = [ctx.level(l, with_internal=True) for l in range(1, 4)]
+            pairs = ctx.step_pairs(0)
+            st = ctx.step_stats(0)
+            assert st["tight_box"] == (0 if opts.get("tight_box") == 0 else 1)
+        if ref_levels is None:
+            ref_levels, ref_pairs = levels, pairs
+            continue
+        for l, (a, b) in enumerate(zip(levels, ref_levels)):
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (opts, l + 1, k)
+        for k in ("parent_idx", "off", "child", "wl", "sumlw"):
+            assert np.array_equal(pairs[k], ref_pairs[k]), (opts, k)
