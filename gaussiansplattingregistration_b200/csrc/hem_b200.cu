@@ -821,16 +821,18 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const bool use_claims = fast || ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && P <= 4 * n && !ctx->dense_hint);
         const bool fuse_claims = use_claims && G == 1 && P > 0;
         if (use_claims && P > 0) {
-            CKR(ensure(ctx, ctx->claims, (size_t)n * CLAIM_K * 8));
+            CKR(ensure(ctx, ctx->claims, (size_t)n * (CLAIM_K1 + CLAIM_K) * 8));      // tier 1 (n x 4), then tier 2 (n x 16)
             CKR(ensure(ctx, ctx->ovf, (size_t)P * 16));
         }
+        uint2* const d_claims = ctx->claims.as<uint2>();
+        uint2* const d_claims2 = d_claims ? d_claims + (size_t)n * CLAIM_K1 : nullptr;
         if (G == 1) {
             if (fast || nchunks > 0) {
                 const int64_t launch_pairs = fast ? (int64_t)pool_cap : P;          // one lane per pool entry
                 pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for(launch_pairs, 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
-                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), PTAB.as<uint2>(), d_cnt_c,
-                    fuse_claims ? ctx->claims.as<uint2>() : nullptr, ctx->ovf.as<uint4>(), (unsigned long long)P,
+                    ctx->pair_off_s.as<uint32_t>(), 0ll, ctx->csr_s.as<uint2>(), ctx->sp0.as<float4>(), PTAB.as<uint2>(), d_cnt_c,
+                    fuse_claims ? d_claims : nullptr, d_claims2, ctx->ovf.as<uint4>(), (unsigned long long)P,
                     launched_gate_heavy ? ctx->seg_off.as<uint32_t>() : nullptr);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
@@ -844,7 +846,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 pdl(k_chunk_copy, (unsigned)std::min<int64_t>(blocks_for(pb[R + 1] - pb[R], 256), (int64_t)ctx->sm_count * 8), 256, 0, st)(
                     ctx->chunks.as<uint4>(), d_counters, (unsigned long long)chunk_cap_used, (unsigned long long)pool_cap, ctx->pool.as<uint2>(),
                     ctx->pair_off_s.as<uint32_t>(), (long long)((int64_t)R * M - pb[R]), ctx->csr_pad.as<uint2>(),
-                    nullptr, nullptr, nullptr, nullptr, 0ull, nullptr);
+                    ctx->sp0.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, 0ull, nullptr);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             CKR(allgather_equal(ctx, ctx->csr_pad.p, 8, M));
@@ -882,14 +884,15 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             const int64_t c_lo = G > 1 ? std::min<int64_t>(cchunk * R, n) : 0, c_hi = G > 1 ? std::min<int64_t>(c_lo + cchunk, n) : n;
             if (!fuse_claims) {
                 pdl(k_claims, blocks_for(np * 32, 256), 256, 0, st)(PTAB.as<uint2>(), ctx->pair_off_s.as<uint32_t>(),
-                                                                    ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, ctx->claims.as<uint2>(),
+                                                                    ctx->csr_s.as<uint2>(), (int)np, d_cnt_c, d_claims, d_claims2,
                                                                     ctx->ovf.as<uint4>(), (unsigned long long)P, fast ? (unsigned long long)pool_cap : ~0ull, d_counters,
                                                                     (uint32_t)c_lo, (uint32_t)c_hi);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             if (c_hi > c_lo) {
-                pdl(k_sumlw_claims, blocks_for(c_hi - c_lo, 256), 256, 0, st)(d_cnt_c, ctx->claims.as<uint2>(), ctx->ovf.as<uint4>(), d_counters,
-                                                                              ctx->sumlw_mode == 2 ? ~0ull : 4096ull, c_lo, c_hi, d_sumlw);
+                pdl(k_sumlw_claims, blocks_for(c_hi - c_lo, 256), 256, 0, st)(d_cnt_c, d_claims, d_claims2, ctx->ovf.as<uint4>(), d_counters,
+                                                                              ctx->sumlw_mode == 2 ? ~0ull : 4096ull, c_lo, c_hi,
+                                                                              fuse_claims ? ctx->sp0.as<float4>() : nullptr, d_sumlw);
                 CK(cudaGetLastError()); ctx->n_launches++;
             }
             if (G > 1) {

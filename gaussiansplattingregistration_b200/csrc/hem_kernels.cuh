@@ -708,7 +708,7 @@ k_gate(GateArgs A)
                     const float colorInfluence = expf(fd(fm(-cdist, cdist), A.decay2));
                     const float L = fm(fm(fm(distWeight, c1.w), colorInfluence), __fsqrt_rn(cdet));
                     const float wl = fm(pw, clamp_ref(L, FLT_MIN, 1e8f));
-                    if (room) A.pool[base + k] = make_uint2(__float_as_uint(c0.w) & 0x7fffffffu, __float_as_uint(wl));
+                    if (room) A.pool[base + k] = make_uint2(jj, __float_as_uint(wl));      // the child's SLOT; k_chunk_copy turns it into its row
                 }
                 if (lane == 0 && cid < A.chunk_cap)
                     A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on | (HEAVY ? (seg_id + 1u) << 8 : 0u), total_out);
@@ -791,6 +791,7 @@ k_gate(GateArgs A)
             const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
+            const float inv_ny = 1.0f / (float)ny;
             // x range of the ellipsoid box (k_ptab; the whole grid when the parent searches its sphere)
             int xlo = 0, xhi = A.g.gx - 1;
             if (p3.w < 3.0e38f) cell_range(p0.x, p3.w, A.g.ox, A.g.inv_h, A.g.gx, xlo, xhi);
@@ -826,7 +827,11 @@ k_gate(GateArgs A)
                 uint32_t ra = 0, len = 0;
                 const int rrow = rb + lane;
                 if (rrow < rb_end) {
-                    const int y = y0 + rrow % ny, z = z0 + rrow / ny;
+                    // rrow = zq * ny + yr without the integer division: float estimate, corrected by one
+                    int zq = (nrows < (1 << 22)) ? (int)(((float)rrow + 0.5f) * inv_ny) : rrow / ny;
+                    int yr = rrow - zq * ny;
+                    if (yr < 0) { --zq; yr += ny; } else if (yr >= ny) { ++zq; yr -= ny; }
+                    const int y = y0 + yr, z = z0 + zq;
                     float lo = A.g.oy + (float)y * hc, hi = lo + hc;
                     float pad = (fabsf(A.g.oy) + fabsf(hi) + hc) * 4e-6f;
                     lo = (y == 0) ? -INF : lo - pad;
@@ -952,57 +957,99 @@ k_gate(GateArgs A)
 // pool -> cell-order CSR (what the moment kernel streams; a rank's slab of parents owns one
 // contiguous segment of it, which is what the ranks exchange).  On one GPU the same pass also files
 // every pair in its child's claim table (see k_claims below), saving a second sweep over the pairs.
-constexpr int CLAIM_K = 16;
+constexpr int CLAIM_K1 = 4;      // first tier: 4 claims = one 32-byte sector per child, consecutive children consecutive sectors
+constexpr int CLAIM_K = 16;      // second tier (children claimed by more than 4 parents), then the global overflow list
 
-__global__ void k_chunk_copy(const uint4* __restrict__ chunks, unsigned long long* __restrict__ counters,
-                             unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
-                             const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s,
-                             const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c, uint2* __restrict__ claims,
-                             uint4* __restrict__ ovf, unsigned long long ovf_cap, const uint32_t* __restrict__ seg_off)
+// file one accepted pair (parent rank, wL bits) under its child; slot order is arbitrary, k_sumlw_claims sorts by rank
+__device__ __forceinline__ void claim_put(uint32_t c, uint32_t srank, uint32_t wl, uint32_t* __restrict__ cnt_c,
+                                          uint2* __restrict__ claims, uint2* __restrict__ claims2, uint4* __restrict__ ovf,
+                                          unsigned long long ovf_cap, unsigned long long* __restrict__ counters)
+{
+    const uint32_t slot = atomicAdd(&cnt_c[c], 1u);
+    if (slot < (uint32_t)CLAIM_K1) {
+        claims[(size_t)c * CLAIM_K1 + slot] = make_uint2(srank, wl);
+    } else if (slot < (uint32_t)(CLAIM_K1 + CLAIM_K)) {
+        claims2[(size_t)c * CLAIM_K + (slot - CLAIM_K1)] = make_uint2(srank, wl);
+    } else {
+        const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+        if (o < ovf_cap) ovf[o] = make_uint4(c, srank, wl, 0u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_chunk_copy(const uint4* __restrict__ chunks, unsigned long long* __restrict__ counters,
+             unsigned long long chunk_cap, unsigned long long pool_cap, const uint2* __restrict__ pool,
+             const uint32_t* __restrict__ pair_off_s, long long dst_shift, uint2* __restrict__ csr_s,
+             const float4* __restrict__ sp0, const uint2* __restrict__ ptab, uint32_t* __restrict__ cnt_c,
+             uint2* __restrict__ claims, uint2* __restrict__ claims2, uint4* __restrict__ ovf,
+             unsigned long long ovf_cap, const uint32_t* __restrict__ seg_off)
 {
     pdl_enter();
     if (pool_overflowed(counters, pool_cap) || (counters[C_POOL] >> POOL_BITS) > chunk_cap) return;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     // One lane per POOL ENTRY (a warp per chunk ran at a quarter of its lanes: a chunk holds ~8 pairs).  Chunk ids and pool
-    // offsets come from the same packed atomic, so the chunk records are sorted by pool offset: a warp finds the chunk of its
-    // first entry by bisection, the chunks that start inside its 32-entry window mark their start lanes, and every lane counts
-    // the marks up to itself.  The counts are read on the device; the launch is sized by the host's upper bound and capped.
+    // offsets come from the same packed atomic, so the chunk records are sorted by pool offset.  A warp takes a run of
+    // CC_RUN consecutive 32-entry windows: it finds the chunk of the run's first entry by a 32-ary search (all lanes probe:
+    // 4 dependent rounds for a million chunks, where a bisection took 20), the chunks that start inside a window mark their
+    // start lanes, every lane counts the marks up to itself, and the chunk of the next window's first entry follows from the
+    // number of marks - its records are in flight while this window is copied.  Runs are dealt round-robin so that the
+    // whole grid sweeps the pool as one front.  The pool holds child SLOTS (cell order): the claim table is indexed by
+    // slot, so that the claims of one child and of its neighbours - filed by parents a few cell rows apart - meet in L2
+    // instead of each costing a 32-byte DRAM read-modify-write; the CSR gets the child's row index (sp0[slot].w).
+    // The counts are read on the device; the launch is sized by the host's upper bound and capped.
+    constexpr unsigned long long CC_RUN = 4;
     const unsigned long long packed = counters[C_POOL];
     const uint32_t nchunks = (uint32_t)min(packed >> POOL_BITS, chunk_cap);
     const unsigned long long npairs = packed & ((1ull << POOL_BITS) - 1ull);
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32ull < npairs; w += nwarps) {
-        const uint32_t e0 = (uint32_t)(w * 32ull);
-        uint32_t lo = 0, hi = nchunks;                      // chunks[lo].y <= e0 < chunks[hi].y
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (chunks[mid].y <= e0) lo = mid; else hi = mid;
+    const unsigned long long nwin = (npairs + 31ull) >> 5;
+    const unsigned long long nruns = (nwin + CC_RUN - 1ull) / CC_RUN;
+    for (unsigned long long run = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; run < nruns; run += nwarps) {
+        const unsigned long long wfirst = run * CC_RUN, wlast = min(nwin, wfirst + CC_RUN);
+        uint32_t lo = 0;
+        {
+            const uint32_t e0 = (uint32_t)(wfirst * 32ull);
+            uint32_t hi = nchunks;                              // chunks[lo].y <= e0 < chunks[hi].y (hi == nchunks: +inf)
+            while (hi - lo > 1) {
+                const uint32_t step = (hi - lo + 32u) / 33u;    // probes at lo + step, lo + 2 step, ..., lo + 32 step
+                const uint32_t idx = lo + (uint32_t)(lane + 1) * step;
+                const bool le = idx < hi && chunks[idx].y <= e0;
+                const uint32_t cnt = (uint32_t)__popc(__ballot_sync(full, le));       // sorted: the lanes that pass are a prefix
+                lo += cnt * step;
+                hi = min(hi, lo + step);
+            }
         }
         uint4 mine = make_uint4(0u, 0u, 0u, 0u);
         if (lo + (uint32_t)lane < nchunks) mine = chunks[lo + lane];
-        const bool inwin = lane > 0 && lo + (uint32_t)lane < nchunks && mine.y - e0 < 32u;      // starts inside the window (lane 0 = the chunk of e0)
-        const unsigned marks = __reduce_or_sync(full, inwin ? (1u << (mine.y - e0)) : 0u);
-        const int src = __popc(marks & ((2u << lane) - 1u));            // chunk of entry e0 + lane, relative to lo (< 32: each chunk has >= 1 pair)
-        uint4 ch;
-        ch.x = __shfl_sync(full, mine.x, src); ch.y = __shfl_sync(full, mine.y, src);
-        ch.z = __shfl_sync(full, mine.z, src); ch.w = __shfl_sync(full, mine.w, src);
-        const unsigned long long e = (unsigned long long)e0 + lane;
-        if (e >= npairs) continue;
-        // a chunk of a heavy parent's segment carries the segment (index + 1) above the count: its prefix is relative to the segment
-        if (ch.z >> 8) ch.w += seg_off[(ch.z >> 8) - 1u];
-        const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w + (size_t)(e - ch.y);    // dst_shift: offset into a rank's padded segment
-        const uint2 p = pool[e];
-        csr_s[dst] = p;
-        if (claims) {
-            const uint32_t srank = ptab[ch.x].y;
-            const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
-            if (slot < (uint32_t)CLAIM_K) {
-                claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
-            } else {
-                const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
-                if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
+        for (unsigned long long w = wfirst; w < wlast; ++w) {
+            const uint32_t e0 = (uint32_t)(w * 32ull);
+            const bool inwin = lane > 0 && lo + (uint32_t)lane < nchunks && mine.y - e0 < 32u;      // starts inside the window (lane 0 = the chunk of e0)
+            const unsigned marks = __reduce_or_sync(full, inwin ? (1u << (mine.y - e0)) : 0u);
+            const int src = __popc(marks & ((2u << lane) - 1u));            // chunk of entry e0 + lane, relative to lo (< 32: each chunk has >= 1 pair)
+            uint4 ch;
+            ch.x = __shfl_sync(full, mine.x, src); ch.y = __shfl_sync(full, mine.y, src);
+            ch.z = __shfl_sync(full, mine.z, src); ch.w = __shfl_sync(full, mine.w, src);
+            if (w + 1 < wlast) {                                // uniform
+                // the chunk of entry e0 + 32: the last one that starts inside this window, or its successor when that one starts at e0 + 32
+                const uint32_t nst = (uint32_t)__popc(marks);
+                uint32_t nlo = lo + nst;
+                uint32_t ny = __shfl_sync(full, mine.y, (int)((nst + 1u) & 31u));
+                if (nst + 1u >= 32u && nlo + 1u < nchunks) ny = chunks[nlo + 1u].y;
+                if (nlo + 1u < nchunks && ny == e0 + 32u) ++nlo;
+                lo = nlo;
+                mine = make_uint4(0u, 0u, 0u, 0u);
+                if (lo + (uint32_t)lane < nchunks) mine = chunks[lo + lane];
             }
+            const unsigned long long e = (unsigned long long)e0 + lane;
+            if (e >= npairs) continue;
+            // a chunk of a heavy parent's segment carries the segment (index + 1) above the count: its prefix is relative to the segment
+            if (ch.z >> 8) ch.w += seg_off[(ch.z >> 8) - 1u];
+            const size_t dst = (size_t)((long long)pair_off_s[ch.x] + dst_shift) + ch.w + (size_t)(e - ch.y);    // dst_shift: offset into a rank's padded segment
+            const uint2 p = pool[e];
+            const uint32_t crow = __float_as_uint(reinterpret_cast<const float*>(sp0)[4 * (size_t)p.x + 3]) & 0x7fffffffu;
+            csr_s[dst] = make_uint2(crow, p.y);
+            if (claims) claim_put(p.x, ptab[ch.x].y, p.y, cnt_c, claims, claims2, ovf, ovf_cap, counters);
         }
     }
 }
@@ -1044,8 +1091,8 @@ __global__ void k_csr_canon(const uint2* __restrict__ ptab, const uint32_t* __re
 
 __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restrict__ pair_off_s,
                          const uint2* __restrict__ csr_s, int np, uint32_t* __restrict__ cnt_c,
-                         uint2* __restrict__ claims, uint4* __restrict__ ovf, unsigned long long ovf_cap,
-                         unsigned long long pool_cap, unsigned long long* __restrict__ counters,
+                         uint2* __restrict__ claims, uint2* __restrict__ claims2, uint4* __restrict__ ovf,
+                         unsigned long long ovf_cap, unsigned long long pool_cap, unsigned long long* __restrict__ counters,
                          uint32_t c_lo, uint32_t c_hi)      // only children in [c_lo, c_hi): this rank's share of the normaliser
 {
     pdl_enter();
@@ -1058,13 +1105,7 @@ __global__ void k_claims(const uint2* __restrict__ ptab, const uint32_t* __restr
     for (uint32_t k = a + lane; k < e; k += 32) {
         const uint2 p = csr_s[k];
         if (p.x < c_lo || p.x >= c_hi) continue;
-        const uint32_t slot = atomicAdd(&cnt_c[p.x], 1u);
-        if (slot < (uint32_t)CLAIM_K) {
-            claims[(size_t)p.x * CLAIM_K + slot] = make_uint2(srank, p.y);
-        } else {
-            const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
-            if (o < ovf_cap) ovf[o] = make_uint4(p.x, srank, p.y, 0u);
-        }
+        claim_put(p.x, srank, p.y, cnt_c, claims, claims2, ovf, ovf_cap, counters);
     }
 }
 
@@ -1080,59 +1121,110 @@ __global__ void k_status_or(unsigned long long* __restrict__ counters, const uns
     counters[C_FAIL] = v;
 }
 
-__global__ void k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ claims,
-                               const uint4* __restrict__ ovf, unsigned long long* __restrict__ counters,
-                               unsigned long long ovf_limit, int64_t c_lo, int64_t n, float* __restrict__ sumlw)
+__global__ void __launch_bounds__(256)
+k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ claims,
+               const uint2* __restrict__ claims2, const uint4* __restrict__ ovf,
+               unsigned long long* __restrict__ counters, unsigned long long ovf_limit, int64_t c_lo, int64_t n,
+               const float4* __restrict__ slot_sp0,      // table indexed by cell-order slot (fused chunk copy): sp0[slot].w = the child's row
+               float* __restrict__ sumlw)
 {
     pdl_enter();
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const int64_t c = c_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // children [c_lo, n)
-    if (c >= n) return;
-    const uint32_t m = cnt_c[c];
-    if (m == 0) return;                                  // orphan: sumLw stays exactly 0
-    const uint2* row = claims + (size_t)c * CLAIM_K;
-    if (m <= 4) {
-        // common case: the claims sit in registers (two 16-byte loads), sorted by a 4-element network
-        // (slots beyond m were never written: read exactly the m entries)
+    const uint32_t m = c < n ? cnt_c[c] : 0u;                                     // 0: orphan, sumLw stays exactly 0
+    const uint2* row = claims + (size_t)c * CLAIM_K1;
+    const uint2* row2 = claims2 + (size_t)c * CLAIM_K;
+    float s = 0.0f;
+    bool have = false;
+#define HEM_CSWAP(ka, wa, kb, wb) { if (kb < ka) { uint32_t t_ = ka; ka = kb; kb = t_; t_ = wa; wa = wb; wb = t_; } }
+    if (m >= 1u && m <= 8u) {
+        // the claims sit in registers (16-byte loads; slots beyond m were never written: masked), sorted by a network
         uint4 a, b = make_uint4(0u, 0u, 0u, 0u);
         if (m >= 2) a = reinterpret_cast<const uint4*>(row)[0];
         else { const uint2 e = row[0]; a = make_uint4(e.x, e.y, 0u, 0u); }
-        if (m == 4) b = reinterpret_cast<const uint4*>(row)[1];
+        if (m >= 4) b = reinterpret_cast<const uint4*>(row)[1];
         else if (m == 3) { const uint2 e = row[2]; b = make_uint4(e.x, e.y, 0u, 0u); }
         uint32_t k0 = a.x, k1 = m > 1 ? a.z : 0xffffffffu, k2 = m > 2 ? b.x : 0xffffffffu, k3 = m > 3 ? b.z : 0xffffffffu;
         uint32_t w0 = a.y, w1 = a.w, w2 = b.y, w3 = b.w;
-#define HEM_CSWAP(ka, wa, kb, wb) { if (kb < ka) { uint32_t t_ = ka; ka = kb; kb = t_; t_ = wa; wa = wb; wb = t_; } }
-        HEM_CSWAP(k0, w0, k1, w1) HEM_CSWAP(k2, w2, k3, w3) HEM_CSWAP(k0, w0, k2, w2) HEM_CSWAP(k1, w1, k3, w3) HEM_CSWAP(k1, w1, k2, w2)
+        if (m <= 4u) {
+            HEM_CSWAP(k0, w0, k1, w1) HEM_CSWAP(k2, w2, k3, w3) HEM_CSWAP(k0, w0, k2, w2) HEM_CSWAP(k1, w1, k3, w3) HEM_CSWAP(k1, w1, k2, w2)
+            s = __uint_as_float(w0);                   // 0 + w0 == w0 exactly (w0 > 0)
+            if (m > 1) s = fa(s, __uint_as_float(w1));
+            if (m > 2) s = fa(s, __uint_as_float(w2));
+            if (m > 3) s = fa(s, __uint_as_float(w3));
+        } else {
+            uint4 cc, d = make_uint4(0u, 0u, 0u, 0u);
+            if (m >= 6) cc = reinterpret_cast<const uint4*>(row2)[0];
+            else { const uint2 e = row2[0]; cc = make_uint4(e.x, e.y, 0u, 0u); }
+            if (m == 8) d = reinterpret_cast<const uint4*>(row2)[1];
+            else if (m == 7) { const uint2 e = row2[2]; d = make_uint4(e.x, e.y, 0u, 0u); }
+            uint32_t k4 = cc.x, k5 = m > 5 ? cc.z : 0xffffffffu, k6 = m > 6 ? d.x : 0xffffffffu, k7 = m > 7 ? d.z : 0xffffffffu;
+            uint32_t w4 = cc.y, w5 = cc.w, w6 = d.y, w7 = d.w;
+            HEM_CSWAP(k0, w0, k1, w1) HEM_CSWAP(k2, w2, k3, w3) HEM_CSWAP(k4, w4, k5, w5) HEM_CSWAP(k6, w6, k7, w7)
+            HEM_CSWAP(k0, w0, k2, w2) HEM_CSWAP(k1, w1, k3, w3) HEM_CSWAP(k4, w4, k6, w6) HEM_CSWAP(k5, w5, k7, w7)
+            HEM_CSWAP(k1, w1, k2, w2) HEM_CSWAP(k5, w5, k6, w6) HEM_CSWAP(k0, w0, k4, w4) HEM_CSWAP(k3, w3, k7, w7)
+            HEM_CSWAP(k1, w1, k5, w5) HEM_CSWAP(k2, w2, k6, w6)
+            HEM_CSWAP(k1, w1, k4, w4) HEM_CSWAP(k3, w3, k6, w6)
+            HEM_CSWAP(k2, w2, k4, w4) HEM_CSWAP(k3, w3, k5, w5)
+            HEM_CSWAP(k3, w3, k4, w4)
+            s = fa(fa(fa(fa(__uint_as_float(w0), __uint_as_float(w1)), __uint_as_float(w2)), __uint_as_float(w3)), __uint_as_float(w4));
+            if (m > 5) s = fa(s, __uint_as_float(w5));
+            if (m > 6) s = fa(s, __uint_as_float(w6));
+            if (m > 7) s = fa(s, __uint_as_float(w7));
+        }
+        have = true;
+    }
 #undef HEM_CSWAP
-        float s = __uint_as_float(w0);                   // 0 + w0 == w0 exactly (w0 > 0)
-        if (m > 1) s = fa(s, __uint_as_float(w1));
-        if (m > 2) s = fa(s, __uint_as_float(w2));
-        if (m > 3) s = fa(s, __uint_as_float(w3));
-        sumlw[c] = s;
-        return;
-    }
-    const uint32_t mt = min(m, (uint32_t)CLAIM_K);
-    const unsigned long long nov = (m > (uint32_t)CLAIM_K) ? counters[C_OVF] : 0ull;
-    if (nov > ovf_limit) {          // dense regime reached the claim table: give up, the host redoes the step by sorting
-        counters[C_FAIL] = 1ull;
-        return;
-    }
-    float s = 0.0f;
-    long long last = -1;
-    for (uint32_t i = 0; i < m; ++i) {                   // selection by ascending parent rank
-        long long best = 0x7fffffffffffffffll;
-        float bw = 0.0f;
-        for (uint32_t k = 0; k < mt; ++k) {
-            const uint2 e = row[k];
-            if ((long long)e.x > last && (long long)e.x < best) { best = e.x; bw = __uint_as_float(e.y); }
+    // 9 .. 20 claims (both tiers): the warp ranks the child's claims together, then adds them in rank order
+    unsigned big = __ballot_sync(full, m > 8u && m <= (uint32_t)(CLAIM_K1 + CLAIM_K));
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int mm = (int)__shfl_sync(full, m, src);
+        const size_t cc = (size_t)(c - lane + src);
+        uint32_t key = 0xffffffffu, wv = 0u;
+        if (lane < mm) {
+            const uint2 e = lane < CLAIM_K1 ? claims[cc * CLAIM_K1 + lane] : claims2[cc * CLAIM_K + (lane - CLAIM_K1)];
+            key = e.x; wv = e.y;
         }
-        for (unsigned long long k = 0; k < nov; ++k) {
-            const uint4 e = ovf[k];
-            if (e.x == (uint32_t)c && (long long)e.y > last && (long long)e.y < best) { best = e.y; bw = __uint_as_float(e.z); }
+        int rank = 0;
+        for (int j = 0; j < mm; ++j) rank += __shfl_sync(full, key, j) < key ? 1 : 0;      // parent ranks are distinct
+        float ss = 0.0f;
+        for (int i = 0; i < mm; ++i) {
+            const unsigned who = __ballot_sync(full, lane < mm && rank == i);
+            ss = fa(ss, __uint_as_float(__shfl_sync(full, wv, __ffs(who) - 1)));
         }
-        s = fa(s, bw);
-        last = best;
+        if (lane == src) { s = ss; have = true; }
     }
-    sumlw[c] = s;
+    if (m > (uint32_t)(CLAIM_K1 + CLAIM_K)) {
+        // beyond both tiers: the rest sits in the global overflow list, which the child scans
+        const unsigned long long nov = counters[C_OVF];
+        if (nov > ovf_limit) {          // dense regime reached the claim table: give up, the host redoes the step by sorting
+            counters[C_FAIL] = 1ull;
+        } else {
+            long long last = -1;
+            for (uint32_t i = 0; i < m; ++i) {                   // selection by ascending parent rank
+                long long best = 0x7fffffffffffffffll;
+                float bw = 0.0f;
+                for (uint32_t k = 0; k < (uint32_t)(CLAIM_K1 + CLAIM_K); ++k) {
+                    const uint2 e = k < (uint32_t)CLAIM_K1 ? row[k] : row2[k - CLAIM_K1];
+                    if ((long long)e.x > last && (long long)e.x < best) { best = e.x; bw = __uint_as_float(e.y); }
+                }
+                for (unsigned long long k = 0; k < nov; ++k) {
+                    const uint4 e = ovf[k];
+                    if (e.x == (uint32_t)c && (long long)e.y > last && (long long)e.y < best) { best = e.y; bw = __uint_as_float(e.z); }
+                }
+                s = fa(s, bw);
+                last = best;
+            }
+            have = true;
+        }
+    }
+    if (have) {
+        const size_t out = slot_sp0 ? (size_t)(__float_as_uint(reinterpret_cast<const float*>(slot_sp0)[4 * (size_t)c + 3]) & 0x7fffffffu) : (size_t)c;
+        sumlw[out] = s;
+    }
 }
 
 // per-child normaliser: pairs stably sorted by child (parents ascending inside a
@@ -1476,17 +1568,50 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
     const bool orphan = i < n && sumlw[i] == 0.0f;
     unsigned m = __ballot_sync(full, orphan);
     const uint32_t myrank = orphan ? orank[i] : 0u;
+    // Rows are copied ORPH_U at a time, all loads of the group issued before the first store: on the
+    // coarse levels most of a warp's 32 rows are orphans and a row-at-a-time loop is one DRAM round
+    // trip per row.
+    constexpr int ORPH_U = 8;
     while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int64_t ci = wbase + src;
-        const size_t dst = (size_t)np + __shfl_sync(full, myrank, src);
-        float4 v;
-        if (lane < 4) v = geo[4 * (size_t)ci + lane];
-        if (lane < 4) ogeo[4 * dst + lane] = v;
-        const float* srow = sh + (size_t)ci * Fp;
-        float* drow = osh + dst * Fp;
-        for (int q = lane; q < Fp; q += 32) drow[q] = srow[q];
+        int srcs[ORPH_U];
+        size_t dsts[ORPH_U];
+#pragma unroll
+        for (int u = 0; u < ORPH_U; ++u) {
+            srcs[u] = m ? __ffs(m) - 1 : -1;
+            m &= m - 1;                                   // 0 stays 0
+            dsts[u] = (size_t)np + __shfl_sync(full, myrank, srcs[u] < 0 ? 0 : srcs[u]);
+        }
+        if (Fp <= 64) {
+            float4 g[ORPH_U];
+            float a[ORPH_U], b[ORPH_U];
+#pragma unroll
+            for (int u = 0; u < ORPH_U; ++u) {
+                if (srcs[u] < 0) continue;
+                const size_t ci = (size_t)(wbase + srcs[u]);
+                if (lane < 4) g[u] = geo[4 * ci + lane];
+                const float* srow = sh + ci * Fp;
+                if (lane < Fp) a[u] = srow[lane];
+                if (lane + 32 < Fp) b[u] = srow[lane + 32];
+            }
+#pragma unroll
+            for (int u = 0; u < ORPH_U; ++u) {
+                if (srcs[u] < 0) continue;
+                if (lane < 4) ogeo[4 * dsts[u] + lane] = g[u];
+                float* drow = osh + dsts[u] * Fp;
+                if (lane < Fp) drow[lane] = a[u];
+                if (lane + 32 < Fp) drow[lane + 32] = b[u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < ORPH_U; ++u) {
+                if (srcs[u] < 0) continue;
+                const size_t ci = (size_t)(wbase + srcs[u]);
+                if (lane < 4) ogeo[4 * dsts[u] + lane] = geo[4 * ci + lane];
+                const float* srow = sh + ci * Fp;
+                float* drow = osh + dsts[u] * Fp;
+                for (int q = lane; q < Fp; q += 32) drow[q] = srow[q];
+            }
+        }
     }
 }
 

@@ -1,10 +1,7 @@
 #!/bin/bash
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-HEM_CELL_SCALE=${CS:-0.5} python - <<'PY'
-import sys; sys.path.insert(0,'.')
-from scripts.gpu_check import timing, check
-ok = check(3000, 20000, 3) & check(20000, 5000, 3) & check(50000, 1000, 2)
-timing(1_000_000, 5000, 5, reps=3)
-timing(3_000_000, 5000, 3, reps=2, aspect=(2,1,0.5))
-print("ALL", "OK" if ok else "MISMATCH")
-PY
+# GPU tests, a short bench (device-resident value only) and the ncu launch list of the same command
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 | tee gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --skip-e2e --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; cut -c1-300 gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_quick.csv python bench.py --steps 1 --warmup 3 --skip-e2e --no-extra --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+tail -1 gpurun_out/ncu_launch.log | cut -c1-200
