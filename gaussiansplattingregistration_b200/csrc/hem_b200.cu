@@ -702,7 +702,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         const bool fast = (G == 1) && !ctx->keep_pairs && guess_claims;
         size_t chunk_cap_used = 0;
         for (int attempt = 0; attempt < 8; ++attempt) {
-            const size_t chunk_cap = (size_t)my_np + pool_cap / (GATE_OUTCAP - 32) + 16;
+            const size_t chunk_cap = 2 * (size_t)my_np + pool_cap / 32 + 16;      // one record per parent present in a batch of 32: <= parents + batches + tickets
             chunk_cap_used = chunk_cap;
             CKR(ensure(ctx, ctx->pool, pool_cap * 8));
             CKR(ensure(ctx, ctx->chunks, chunk_cap * 16));

@@ -516,13 +516,13 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
 #define HEM_GATE_MINBLOCKS 4
 #endif
 #ifndef HEM_GATE_TB
-#define HEM_GATE_TB 4
+#define HEM_GATE_TB 8
 #endif
 #ifndef HEM_MOM_B
 #define HEM_MOM_B 8
 #endif
 constexpr int GATE_WARPS = 8;
-constexpr int GATE_OUTCAP = 128;
+constexpr int GATE_OUTCAP = 64;         // accepted children waiting for the likelihood: flushed 32 at a time, so < 32 + 32
 constexpr int GATE_TB = HEM_GATE_TB;        // parents per work ticket
 // pool and chunk counters share one 64-bit word: pairs in the low 40 bits, chunks above
 constexpr int POOL_BITS = 40;
@@ -634,10 +634,14 @@ k_gate(GateArgs A)
     __shared__ uint32_t s_q[GATE_WARPS][64];
     __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
     __shared__ uint2 s_q2[GATE_WARPS][64];
+    __shared__ uint8_t s_otag[GATE_WARPS][GATE_OUTCAP];         // which parent of the ticket an accepted child belongs to
+    __shared__ float4 s_pc[GATE_WARPS][GATE_TB][2];             // per parent of the ticket: (mean, weight), (colour, bits(t))
+    __shared__ uint32_t s_tot[GATE_WARPS][GATE_TB];             // pairs of that parent already in the pool
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* q = s_q[warp];
     uint32_t* ob = s_out[warp];
+    uint8_t* otag = s_otag[warp];
     uint2* q2 = s_q2[warp];
     const float hc = A.g.h;
     const float INF = __uint_as_float(0x7f800000u);
@@ -670,6 +674,55 @@ k_gate(GateArgs A)
             seg_n = si.z;
             seg_first = si.w;
         }
+      // Accepted children of ALL the ticket's parents wait in `ob` (a parent accepts ~8: a flush per parent ran the
+      // likelihood on a quarter of the lanes); they leave 32 at a time, each with its parent's constants from shared
+      // memory, one chunk record per parent present in the batch.
+      int on = 0;
+      auto flush32 = [&]() {
+          const int nb = min(on, 32);
+          uint32_t jj = 0, tg = 0;
+          if (lane < nb) { jj = ob[lane]; tg = otag[lane]; }
+          const uint32_t tg_prev = __shfl_up_sync(full, tg, 1);
+          const bool head = lane < nb && (lane == 0 || tg != tg_prev);
+          const unsigned hb = __ballot_sync(full, head);
+          unsigned long long base = 0, cid = 0;
+          if (lane == 0) {
+              const unsigned long long v = atomicAdd(&A.counters[C_POOL], ((unsigned long long)__popc(hb) << POOL_BITS) | (unsigned long long)nb);
+              base = v & ((1ull << POOL_BITS) - 1ull);
+              cid = v >> POOL_BITS;
+          }
+          base = __shfl_sync(full, base, 0);
+          cid = __shfl_sync(full, cid, 0);
+          const bool room = base + (unsigned long long)nb <= A.pool_cap;
+          if (lane < nb) {
+              const float4 q0 = s_pc[warp][tg][0], q1 = s_pc[warp][tg][1];
+              const float4 c0 = A.sp0[jj], c1 = A.sp1[jj];
+              const float cdet = A.sp3[jj].z;
+              // hemLikelihoodOpacity, mixture.cpp:54-64; clamp + parent weight, :155-156
+              const float dd = __fsqrt_rn(sqdist3(q0.x, q0.y, q0.z, c0.x, c0.y, c0.z));
+              const float cdist = __fsqrt_rn(sqdist3(q1.x, q1.y, q1.z, c1.x, c1.y, c1.z));
+              const float distWeight = expf(fd(fm(-dd, dd), A.decay2));
+              const float colorInfluence = expf(fd(fm(-cdist, cdist), A.decay2));
+              const float L = fm(fm(fm(distWeight, c1.w), colorInfluence), __fsqrt_rn(cdet));
+              const float wl = fm(q0.w, clamp_ref(L, FLT_MIN, 1e8f));
+              if (room) A.pool[base + lane] = make_uint2(jj, __float_as_uint(wl));      // the child's SLOT; k_chunk_copy turns it into its row
+              if (head) {
+                  const unsigned later = hb & ~((2u << lane) - 1u);
+                  const uint32_t cnt = (uint32_t)((later ? __ffs(later) - 1 : nb) - lane);
+                  const unsigned long long id = cid + (unsigned long long)__popc(hb & ((1u << lane) - 1u));
+                  const uint32_t pre = s_tot[warp][tg];
+                  if (id < A.chunk_cap)
+                      A.chunks[id] = make_uint4(__float_as_uint(q1.w), (uint32_t)base + (uint32_t)lane, cnt | (HEAVY ? (seg_id + 1u) << 8 : 0u), pre);
+                  s_tot[warp][tg] = pre + cnt;
+              }
+          }
+          const uint32_t mv = (lane + 32 < on) ? ob[lane + 32] : 0u;
+          const uint8_t mt = (lane + 32 < on) ? otag[lane + 32] : (uint8_t)0;
+          __syncwarp();
+          ob[lane] = mv; otag[lane] = mt;
+          on -= nb;
+          __syncwarp();
+      };
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
@@ -682,41 +735,15 @@ k_gate(GateArgs A)
         const Sym3 ip = { p5.x, p5.y, p5.z, p5.w, p6.x, p6.y };
 
         const bool pcert = (__float_as_uint(p4.z) >> 31) != 0;
-        int qn = 0, q2n = 0, on = 0;
+        int qn = 0, q2n = 0;
         uint32_t total_out = 0;
-
-        // accepted children wait in `ob` as sorted slots; the likelihood is evaluated here, on
-        // compacted lanes, once per flush instead of once per candidate batch
-        auto flush = [&]() {
-            if (on > 0) {
-                unsigned long long base = 0, cid = 0;
-                if (lane == 0) {
-                    const unsigned long long v = atomicAdd(&A.counters[C_POOL], (1ull << POOL_BITS) | (unsigned long long)on);
-                    base = v & ((1ull << POOL_BITS) - 1ull);
-                    cid = v >> POOL_BITS;
-                }
-                base = __shfl_sync(full, base, 0);
-                const bool room = base + (unsigned long long)on <= A.pool_cap;
-                for (int k = lane; k < on; k += 32) {
-                    const uint32_t jj = ob[k];
-                    const float4 c0 = A.sp0[jj], c1 = A.sp1[jj];
-                    const float cdet = A.sp3[jj].z;
-                    // hemLikelihoodOpacity, mixture.cpp:54-64; clamp + parent weight, :155-156
-                    const float dd = __fsqrt_rn(sqdist3(p0.x, p0.y, p0.z, c0.x, c0.y, c0.z));
-                    const float cdist = __fsqrt_rn(sqdist3(p1.x, p1.y, p1.z, c1.x, c1.y, c1.z));
-                    const float distWeight = expf(fd(fm(-dd, dd), A.decay2));
-                    const float colorInfluence = expf(fd(fm(-cdist, cdist), A.decay2));
-                    const float L = fm(fm(fm(distWeight, c1.w), colorInfluence), __fsqrt_rn(cdet));
-                    const float wl = fm(pw, clamp_ref(L, FLT_MIN, 1e8f));
-                    if (room) A.pool[base + k] = make_uint2(jj, __float_as_uint(wl));      // the child's SLOT; k_chunk_copy turns it into its row
-                }
-                if (lane == 0 && cid < A.chunk_cap)
-                    A.chunks[cid] = make_uint4((uint32_t)t, (uint32_t)base, (uint32_t)on | (HEAVY ? (seg_id + 1u) << 8 : 0u), total_out);
-                total_out += (uint32_t)on;
-                on = 0;
-                __syncwarp();
-            }
-        };
+        const uint32_t tslot = (uint32_t)(t - tfirst);
+        if (lane == 0) {
+            s_pc[warp][tslot][0] = make_float4(p0.x, p0.y, p0.z, pw);
+            s_pc[warp][tslot][1] = make_float4(p1.x, p1.y, p1.z, __uint_as_float((uint32_t)t));
+            s_tot[warp][tslot] = 0u;
+        }
+        __syncwarp();
 
         // candidates that passed the radius + parent-exclusion test: colour gate, KLD gate, likelihood
         // stage B: candidates that survived colour gate and smd pre-test: trace, log-det, KLD gate
@@ -737,10 +764,14 @@ k_gate(GateArgs A)
                 acc = !(kl > A.kthr);
             }
             const unsigned am = __ballot_sync(full, acc);
-            if (acc) ob[on + __popc(am & ((1u << lane) - 1u))] = jj;
+            if (acc) {
+                const int pos = on + __popc(am & ((1u << lane) - 1u));
+                ob[pos] = jj; otag[pos] = (uint8_t)tslot;
+            }
             on += __popc(am);
+            total_out += (uint32_t)__popc(am);
             __syncwarp();
-            if (on > GATE_OUTCAP - 32) flush();
+            if (on >= 32) flush32();
         };
         // stage A: candidates that passed the radius + parent-exclusion test: colour gate, squared
         // Mahalanobis distance, certified pre-test (hem_math.cuh); survivors queue for stage B
@@ -910,7 +941,6 @@ k_gate(GateArgs A)
             }
             if (qn > 0) process(qn);
             if (q2n > 0) stage_b(q2n);
-            flush();
         }
         if (!HEAVY) {
             if (lane == 0) {
@@ -951,6 +981,7 @@ k_gate(GateArgs A)
         }
         __syncwarp();
       }
+      if (on > 0) flush32();        // what the ticket's last parents left behind (< 32)
     }
 }
 
