@@ -634,14 +634,19 @@ k_gate(GateArgs A)
     __shared__ uint32_t s_q[GATE_WARPS][64];
     __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
     __shared__ uint2 s_q2[GATE_WARPS][64];
-    __shared__ uint8_t s_otag[GATE_WARPS][GATE_OUTCAP];         // which parent of the ticket an accepted child belongs to
-    __shared__ float4 s_pc[GATE_WARPS][GATE_TB][2];             // per parent of the ticket: (mean, weight), (colour, bits(t))
+    // which parent of the ticket a queued candidate belongs to (the three queues run across the ticket's parents)
+    __shared__ uint8_t s_qtag[GATE_WARPS][64], s_q2tag[GATE_WARPS][64], s_otag[GATE_WARPS][GATE_OUTCAP];
+    // per parent of the ticket: (mean, weight), (colour, bits(t)), (ip00, ip01, ip02, ip11), (ip12, ip22, det, bits(rank | certified << 31))
+    __shared__ float4 s_pc[GATE_WARPS][GATE_TB][4];
     __shared__ uint32_t s_tot[GATE_WARPS][GATE_TB];             // pairs of that parent already in the pool
+    __shared__ uint32_t s_acc[GATE_WARPS][GATE_TB];             // pairs of that parent accepted so far (~0: left to k_gate<true>)
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* q = s_q[warp];
     uint32_t* ob = s_out[warp];
     uint8_t* otag = s_otag[warp];
+    uint8_t* qtag = s_qtag[warp];
+    uint8_t* q2tag = s_q2tag[warp];
     uint2* q2 = s_q2[warp];
     const float hc = A.g.h;
     const float INF = __uint_as_float(0x7f800000u);
@@ -674,10 +679,11 @@ k_gate(GateArgs A)
             seg_n = si.z;
             seg_first = si.w;
         }
-      // Accepted children of ALL the ticket's parents wait in `ob` (a parent accepts ~8: a flush per parent ran the
-      // likelihood on a quarter of the lanes); they leave 32 at a time, each with its parent's constants from shared
-      // memory, one chunk record per parent present in the batch.
-      int on = 0;
+      // The three queues (in radius -> stage A -> stage B -> likelihood) run across ALL the ticket's parents: a parent
+      // has ~35 candidates in radius, ~15 after stage A and accepts ~8, so a drain per parent ran the stages on 55 % /
+      // 47 % / 25 % of the lanes.  Entries carry the parent's position in the ticket and leave 32 at a time, each with
+      // its parent's constants from shared memory; the pool gets one chunk record per parent present in a batch.
+      int qn = 0, q2n = 0, on = 0;
       auto flush32 = [&]() {
           const int nb = min(on, 32);
           uint32_t jj = 0, tg = 0;
@@ -723,95 +729,117 @@ k_gate(GateArgs A)
           on -= nb;
           __syncwarp();
       };
+      // stage B: candidates that survived the smd pre-test and the colour gate: trace, log-det, KLD gate
+      auto stage_b = [&](int m) {
+          bool acc = false;
+          uint32_t jj = 0, tg = 0;
+          if (lane < m) {
+              const uint2 e = q2[lane];
+              tg = q2tag[lane];
+              jj = e.x;
+              const float smd = __uint_as_float(e.y);
+              const float4 i0 = s_pc[warp][tg][2], i1 = s_pc[warp][tg][3];       // (ip00, ip01, ip02, ip11), (ip12, ip22, det, .)
+              const float4 c2 = A.sp2[jj], c3 = A.sp3[jj];
+              const float t00 = fa(fa(fm(c2.x, i0.x), fm(c2.y, i0.y)), fm(c2.z, i0.z));
+              const float t11 = fa(fa(fm(c2.y, i0.y), fm(c2.w, i0.w)), fm(c3.x, i1.x));
+              const float t22 = fa(fa(fm(c2.z, i0.z), fm(c3.x, i1.x)), fm(c3.y, i1.y));
+              const float tr = fa(fa(t00, t11), t22);
+              // KLD(child || parent), gaussian.hpp:106-109
+              const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(c3.z, i1.z))));
+              acc = !(kl > A.kthr);
+          }
+          const unsigned am = __ballot_sync(full, acc);
+          if (acc) {
+              const int pos = on + __popc(am & ((1u << lane) - 1u));
+              ob[pos] = jj; otag[pos] = (uint8_t)tg;
+          }
+          // accepted pairs per parent: the first lane of each parent's run counts its run
+          const uint32_t tg_prev = __shfl_up_sync(full, tg, 1);
+          const bool head = lane < m && (lane == 0 || tg != tg_prev);
+          const unsigned hb = __ballot_sync(full, head);
+          if (head) {
+              const unsigned later = hb & ~((2u << lane) - 1u);
+              const int end = later ? __ffs(later) - 1 : m;
+              const unsigned span = (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << lane) - 1u);
+              s_acc[warp][tg] += (uint32_t)__popc(am & span);
+          }
+          on += __popc(am);
+          __syncwarp();
+          if (on >= 32) flush32();
+      };
+      // stage A: candidates that passed the radius + parent-exclusion test: squared Mahalanobis distance with the
+      // certified pre-test (hem_math.cuh), colour gate; survivors queue for stage B
+      auto process = [&](int m) {
+          bool keep = false;
+          uint32_t jj = 0, tg = 0;
+          float smd = 0.0f;
+          if (lane < m) {
+              jj = q[lane];
+              tg = qtag[lane];
+              const float4 c0 = A.sp0[jj];
+              const float4 q0 = s_pc[warp][tg][0], i0 = s_pc[warp][tg][2], i1 = s_pc[warp][tg][3];
+              // Both gates must pass, so their order is free: the Mahalanobis pre-test goes first (it rejects more than
+              // half of what reaches this stage and needs nothing but the mean), the colour row is fetched for the rest.
+              const float dx = fs(c0.x, q0.x), dy = fs(c0.y, q0.y), dz = fs(c0.z, q0.z);
+              const float tx = fa(fa(fm(i0.x, dx), fm(i0.y, dy)), fm(i0.z, dz));
+              const float ty = fa(fa(fm(i0.y, dx), fm(i0.w, dy)), fm(i1.x, dz));
+              const float tz = fa(fa(fm(i0.z, dx), fm(i1.x, dy)), fm(i1.y, dz));
+              smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
+              bool rej = false;
+              if ((__float_as_uint(i1.w) >> 31) != 0u && smd > A.smd_rej)          // certified pre-test (hem_math.cuh): needs a certified candidate as well
+                  rej = A.all_cert || __float_as_uint(A.sp3[jj].w) != 0u;
+              if (!rej) {
+                  // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
+                  const float4 c1 = A.sp1[jj];
+                  const float4 q1 = s_pc[warp][tg][1];
+                  const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, q1.x, q1.y, q1.z));
+                  keep = !(cdist > A.cthr);
+              }
+          }
+          const unsigned km = __ballot_sync(full, keep);
+          if (keep) {
+              const int pos = q2n + __popc(km & ((1u << lane) - 1u));
+              q2[pos] = make_uint2(jj, __float_as_uint(smd)); q2tag[pos] = (uint8_t)tg;
+          }
+          q2n += __popc(km);
+          __syncwarp();
+          if (q2n >= 32) {
+              stage_b(32);
+              const uint2 mv = (lane + 32 < q2n) ? q2[lane + 32] : make_uint2(0u, 0u);
+              const uint8_t mt = (lane + 32 < q2n) ? q2tag[lane + 32] : (uint8_t)0;
+              __syncwarp();
+              q2[lane] = mv; q2tag[lane] = mt;
+              q2n -= 32;
+              __syncwarp();
+          }
+      };
+      // a full batch of in-radius candidates goes through stage A
+      auto q_drain32 = [&]() {
+          process(32);
+          const uint32_t mv = (lane + 32 < qn) ? q[lane + 32] : 0u;
+          const uint8_t mt = (lane + 32 < qn) ? qtag[lane + 32] : (uint8_t)0;
+          __syncwarp();
+          q[lane] = mv; qtag[lane] = mt;
+          qn -= 32;
+          __syncwarp();
+      };
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
         const float4 p0 = pi[0], p1 = pi[1], p3 = pi[3], p4 = pi[4], p5 = pi[5], p6 = pi[6];
-        const uint32_t s = __float_as_uint(p4.w);
         const float rad = p4.x;
-        const float pw = p4.y;
         const float r2 = fm(rad, rad);
-        const float pdet = p3.z;
-        const Sym3 ip = { p5.x, p5.y, p5.z, p5.w, p6.x, p6.y };
 
-        const bool pcert = (__float_as_uint(p4.z) >> 31) != 0;
-        int qn = 0, q2n = 0;
-        uint32_t total_out = 0;
         const uint32_t tslot = (uint32_t)(t - tfirst);
         if (lane == 0) {
-            s_pc[warp][tslot][0] = make_float4(p0.x, p0.y, p0.z, pw);
+            s_pc[warp][tslot][0] = make_float4(p0.x, p0.y, p0.z, p4.y);
             s_pc[warp][tslot][1] = make_float4(p1.x, p1.y, p1.z, __uint_as_float((uint32_t)t));
+            s_pc[warp][tslot][2] = p5;
+            s_pc[warp][tslot][3] = make_float4(p6.x, p6.y, p3.z, p4.z);
             s_tot[warp][tslot] = 0u;
+            s_acc[warp][tslot] = 0u;
         }
         __syncwarp();
-
-        // candidates that passed the radius + parent-exclusion test: colour gate, KLD gate, likelihood
-        // stage B: candidates that survived colour gate and smd pre-test: trace, log-det, KLD gate
-        auto stage_b = [&](int m) {
-            bool acc = false;
-            uint32_t jj = 0;
-            if (lane < m) {
-                const uint2 e = q2[lane];
-                jj = e.x;
-                const float smd = __uint_as_float(e.y);
-                const float4 c2 = A.sp2[jj], c3 = A.sp3[jj];
-                const float t00 = fa(fa(fm(c2.x, ip.e00), fm(c2.y, ip.e01)), fm(c2.z, ip.e02));
-                const float t11 = fa(fa(fm(c2.y, ip.e01), fm(c2.w, ip.e11)), fm(c3.x, ip.e12));
-                const float t22 = fa(fa(fm(c2.z, ip.e02), fm(c3.x, ip.e12)), fm(c3.y, ip.e22));
-                const float tr = fa(fa(t00, t11), t22);
-                // KLD(child || parent), gaussian.hpp:106-109
-                const float kl = fm(0.5f, fs(fs(fa(smd, tr), 3.0f), logf_glibc(fd(c3.z, pdet))));
-                acc = !(kl > A.kthr);
-            }
-            const unsigned am = __ballot_sync(full, acc);
-            if (acc) {
-                const int pos = on + __popc(am & ((1u << lane) - 1u));
-                ob[pos] = jj; otag[pos] = (uint8_t)tslot;
-            }
-            on += __popc(am);
-            total_out += (uint32_t)__popc(am);
-            __syncwarp();
-            if (on >= 32) flush32();
-        };
-        // stage A: candidates that passed the radius + parent-exclusion test: colour gate, squared
-        // Mahalanobis distance, certified pre-test (hem_math.cuh); survivors queue for stage B
-        auto process = [&](int m) {
-            bool keep = false;
-            uint32_t jj = 0;
-            float smd = 0.0f;
-            if (lane < m) {
-                jj = q[lane];
-                const float4 c0 = A.sp0[jj];
-                // Both gates must pass, so their order is free: the Mahalanobis pre-test goes first (it rejects more than
-                // half of what reaches this stage and needs nothing but the mean), the colour row is fetched for the rest.
-                const float dx = fs(c0.x, p0.x), dy = fs(c0.y, p0.y), dz = fs(c0.z, p0.z);
-                const float tx = fa(fa(fm(ip.e00, dx), fm(ip.e01, dy)), fm(ip.e02, dz));
-                const float ty = fa(fa(fm(ip.e01, dx), fm(ip.e11, dy)), fm(ip.e12, dz));
-                const float tz = fa(fa(fm(ip.e02, dx), fm(ip.e12, dy)), fm(ip.e22, dz));
-                smd = fa(fa(fm(dx, tx), fm(dy, ty)), fm(dz, tz));
-                bool rej = false;
-                if (pcert && smd > A.smd_rej)          // certified pre-test (hem_math.cuh): needs a certified candidate as well
-                    rej = A.all_cert || __float_as_uint(A.sp3[jj].w) != 0u;
-                if (!rej) {
-                    // colour gate, mixture.cpp:121-124 / gaussian.hpp:111-114 (NaN passes)
-                    const float4 c1 = A.sp1[jj];
-                    const float cdist = __fsqrt_rn(sqdist3(c1.x, c1.y, c1.z, p1.x, p1.y, p1.z));
-                    keep = !(cdist > A.cthr);
-                }
-            }
-            const unsigned km = __ballot_sync(full, keep);
-            if (keep) q2[q2n + __popc(km & ((1u << lane) - 1u))] = make_uint2(jj, __float_as_uint(smd));
-            q2n += __popc(km);
-            __syncwarp();
-            if (q2n >= 32) {
-                stage_b(32);
-                const uint2 mv = (lane + 32 < q2n) ? q2[lane + 32] : make_uint2(0u, 0u);
-                __syncwarp();
-                q2[lane] = mv;
-                q2n -= 32;
-                __syncwarp();
-            }
-        };
 
         if (rad > 0.0f) {        // NaN / zero radius: no child can pass `d2 < r*r` (pointindex.cpp:138)
             // conservative cell box (DESIGN.md "grid range"): the float test can only pass for
@@ -837,6 +865,8 @@ k_gate(GateArgs A)
                     sb = __shfl_sync(full, sb, 0);
                     if (sb + ns <= A.seg_cap)
                         for (uint32_t k = lane; k < ns; k += 32) A.seg_info[sb + k] = make_uint4((uint32_t)t, k, ns, sb);
+                    if (lane == 0) s_acc[warp][tslot] = 0xffffffffu;     // its pair count is k_gate<true>'s to write
+                    __syncwarp();
                     continue;
                 }
             }
@@ -845,9 +875,10 @@ k_gate(GateArgs A)
             // the colour / KLD gates are evaluated on it like on any other candidate.
             // (the test is spelled out on the parent's own coordinates: a NaN / infinite mean fails it, as in the reference)
             if (sqdist3(p0.x, p0.y, p0.z, p0.x, p0.y, p0.z) < r2 && (!HEAVY || seg_local == 0u)) {
-                if (lane == 0) q[0] = A.nc + (uint32_t)t;
-                qn = 1;
+                if (lane == 0) { q[qn] = A.nc + (uint32_t)t; qtag[qn] = (uint8_t)tslot; }
+                qn += 1;
                 __syncwarp();
+                if (qn >= 32) q_drain32();
             }
             const int rb_begin = HEAVY ? (int)seg_local * GATE_SEG_ROWS : 0;
             const int rb_end = HEAVY ? min(nrows, rb_begin + GATE_SEG_ROWS) : nrows;
@@ -926,26 +957,33 @@ k_gate(GateArgs A)
                         in = d2 < r2;
                     }
                     const unsigned m = __ballot_sync(full, in);
-                    if (in) q[qn + __popc(m & ((1u << lane) - 1u))] = jj;
+                    if (in) {
+                        const int pos = qn + __popc(m & ((1u << lane) - 1u));
+                        q[pos] = jj; qtag[pos] = (uint8_t)tslot;
+                    }
                     qn += __popc(m);
                     __syncwarp();
-                    if (qn >= 32) {
-                        process(32);
-                        const uint32_t mv = (lane + 32 < qn) ? q[lane + 32] : 0u;
-                        __syncwarp();
-                        q[lane] = mv;
-                        qn -= 32;
-                        __syncwarp();
-                    }
+                    if (qn >= 32) q_drain32();
                 }
             }
-            if (qn > 0) process(qn);
-            if (q2n > 0) stage_b(q2n);
         }
+      }
+      // end of the ticket: what its parents left in the queues
+      if (qn > 0) { process(qn); qn = 0; }
+      if (q2n > 0) { stage_b(q2n); q2n = 0; }
+      if (on > 0) flush32();        // (< 32)
+      __syncwarp();
+      {
+        const int t = tfirst;
+        const uint32_t total_out = s_acc[warp][0];
+        const uint32_t rank0 = __float_as_uint(s_pc[warp][0][3].w) & 0x7fffffffu;
         if (!HEAVY) {
-            if (lane == 0) {
-                A.pair_cnt_s[t] = total_out;
-                if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = total_out;
+            if (lane < tlast - tfirst) {
+                const uint32_t cnt = s_acc[warp][lane];
+                if (cnt != 0xffffffffu) {
+                    A.pair_cnt_s[tfirst + lane] = cnt;
+                    if (A.pair_cnt) A.pair_cnt[__float_as_uint(s_pc[warp][lane][3].w) & 0x7fffffffu] = cnt;
+                }
             }
         } else {
             // the segment's count; the warp that finishes the parent's last segment turns the counts into offsets
@@ -974,14 +1012,13 @@ k_gate(GateArgs A)
                 }
                 if (lane == 0) {
                     A.pair_cnt_s[t] = run;
-                    if (A.pair_cnt) A.pair_cnt[__float_as_uint(p4.z) & 0x7fffffffu] = run;
+                    if (A.pair_cnt) A.pair_cnt[rank0] = run;
                     A.seg_done[t] = 0u;
                 }
             }
         }
         __syncwarp();
       }
-      if (on > 0) flush32();        // what the ticket's last parents left behind (< 32)
     }
 }
 
