@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(GATE_WARPS * 32, HEM_GATE_MINBLOCKS)
 k_gate(GateArgs A)
 {
     pdl_enter();
-    __shared__ uint32_t s_q[GATE_WARPS][64];
+    __shared__ float4 s_q[GATE_WARPS][64];                      // in-radius candidates: (mean, bits(slot)) - stage A needs nothing else of the row
     __shared__ uint32_t s_out[GATE_WARPS][GATE_OUTCAP];
     __shared__ uint2 s_q2[GATE_WARPS][64];
     // which parent of the ticket a queued candidate belongs to (the three queues run across the ticket's parents)
@@ -642,7 +642,7 @@ k_gate(GateArgs A)
     __shared__ uint32_t s_acc[GATE_WARPS][GATE_TB];             // pairs of that parent accepted so far (~0: left to k_gate<true>)
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* q = s_q[warp];
+    float4* q = s_q[warp];
     uint32_t* ob = s_out[warp];
     uint8_t* otag = s_otag[warp];
     uint8_t* qtag = s_qtag[warp];
@@ -774,9 +774,9 @@ k_gate(GateArgs A)
           uint32_t jj = 0, tg = 0;
           float smd = 0.0f;
           if (lane < m) {
-              jj = q[lane];
+              const float4 c0 = q[lane];
+              jj = __float_as_uint(c0.w);
               tg = qtag[lane];
-              const float4 c0 = A.sp0[jj];
               const float4 q0 = s_pc[warp][tg][0], i0 = s_pc[warp][tg][2], i1 = s_pc[warp][tg][3];
               // Both gates must pass, so their order is free: the Mahalanobis pre-test goes first (it rejects more than
               // half of what reaches this stage and needs nothing but the mean), the colour row is fetched for the rest.
@@ -816,7 +816,7 @@ k_gate(GateArgs A)
       // a full batch of in-radius candidates goes through stage A
       auto q_drain32 = [&]() {
           process(32);
-          const uint32_t mv = (lane + 32 < qn) ? q[lane + 32] : 0u;
+          const float4 mv = (lane + 32 < qn) ? q[lane + 32] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           const uint8_t mt = (lane + 32 < qn) ? qtag[lane + 32] : (uint8_t)0;
           __syncwarp();
           q[lane] = mv; qtag[lane] = mt;
@@ -875,7 +875,7 @@ k_gate(GateArgs A)
             // the colour / KLD gates are evaluated on it like on any other candidate.
             // (the test is spelled out on the parent's own coordinates: a NaN / infinite mean fails it, as in the reference)
             if (sqdist3(p0.x, p0.y, p0.z, p0.x, p0.y, p0.z) < r2 && (!HEAVY || seg_local == 0u)) {
-                if (lane == 0) { q[qn] = A.nc + (uint32_t)t; qtag[qn] = (uint8_t)tslot; }
+                if (lane == 0) { q[qn] = make_float4(p0.x, p0.y, p0.z, __uint_as_float(A.nc + (uint32_t)t)); qtag[qn] = (uint8_t)tslot; }
                 qn += 1;
                 __syncwarp();
                 if (qn >= 32) q_drain32();
@@ -959,7 +959,7 @@ k_gate(GateArgs A)
                     const unsigned m = __ballot_sync(full, in);
                     if (in) {
                         const int pos = qn + __popc(m & ((1u << lane) - 1u));
-                        q[pos] = jj; qtag[pos] = (uint8_t)tslot;
+                        q[pos] = make_float4(c0.x, c0.y, c0.z, __uint_as_float(jj)); qtag[pos] = (uint8_t)tslot;
                     }
                     qn += __popc(m);
                     __syncwarp();
