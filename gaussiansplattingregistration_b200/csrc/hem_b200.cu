@@ -59,7 +59,8 @@ struct StepStats {
     int64_t n_parents_local = 0, n_pairs_local = 0;   // this rank's share of the gate / moment work (multi-GPU)
     int shards = 1;                                   // ranks the step was sharded over
     bool tight = false;                               // ellipsoid boxes were used
-    bool timed = false, timed_pairs = false;          // events of this step were recorded (read at the end of the build)
+    int timed = 0;                                    // events of this step were recorded (ctx->timing at the time)
+    bool timed_pairs = false, ms_read = true;         // ... and are still to be turned into ms[] (on the first hem_step_stats)
     double cell_size = 0, max_radius = 0;
     double ms_host = 0;       // host time spent enqueueing the step (up to its closing sync)
     double ms[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // total, prep, grid, gate, sumlw, moments, compact, k_gate, k_moments
@@ -80,7 +81,8 @@ struct hem_ctx {
     uint64_t seed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
-    bool timing = false, keep_pairs = false, smd_prefilter = true;
+    int timing = 0;                             // 0 off, 1 events around every stage, 2 only the level and the two hot kernels
+    bool keep_pairs = false, smd_prefilter = true;
     bool tight_box = true;         // certified parents search the box of their Mahalanobis ellipsoid when no component of the level is uncertified
     int sumlw_mode = 0;            // 0 auto, 1 radix sort, 2 claim table
     // prep of the next level carried over from k_finish (no prep kernel, no host sync)
@@ -126,6 +128,10 @@ struct hem_ctx {
     unsigned long long* h_counters = nullptr;   // pinned
     Ctl* h_ctl = nullptr;                       // pinned + mapped: kernels publish the control block into it
     Ctl* h_ctl_dev = nullptr;                   // device alias of h_ctl
+    unsigned* h_seq = nullptr;                  // pinned + mapped: k_publish's "block is visible" word, polled by the host
+    unsigned* h_seq_dev = nullptr;
+    unsigned seq_next = 1;
+    bool poll_sync = true;                      // end-of-level wait: poll h_seq instead of cudaStreamSynchronize
     // timing events, one set per level: recorded while the steps run, read once at the end of the build (a readout per
     // step cost an extra event synchronisation per level)
     std::vector<std::vector<cudaEvent_t>> evs;
@@ -531,7 +537,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         pdl(k_prep, (unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st)(
             geo, n, distance_delta, RAD.as<float>(), PFLAG.as<uint32_t>(), SAFE.as<uint8_t>(), d_ctl);
         CK(cudaGetLastError()); ctx->n_launches++;
-        pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
+        pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev, (unsigned*)nullptr, 0u);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));                                  // sync A (level 0 / after an erasing filter only)
         ps = *ctx->h_ctl;
@@ -551,7 +557,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     float max_radius = 0.0f;
     memcpy(&max_radius, &ps.max_radius_bits, 4);
     S.max_radius = max_radius;
-    if (ctx->timing) CK(cudaEventRecord(ev[EV_PREP], st));
+    if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_PREP], st));
 
     // next level store: upper bound n + np rows (a NaN-radius parent is both a merged row and an orphan)
     const int64_t cap_rows = n + np;
@@ -668,7 +674,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                              ctx->cell_start.as<uint32_t>());
         CK(cudaGetLastError()); ctx->n_launches++;
         CKR(join1());
-        if (ctx->timing) CK(cudaEventRecord(ev[EV_GRID], st));
+        if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
         nvtx.next("S3 gate");
@@ -779,7 +785,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                 }));
             }
             if (fast) break;
-            pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
+            pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev, (unsigned*)nullptr, 0u);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));                              // sync B
             memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
@@ -855,7 +861,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                     CK(cudaMemcpyAsync(ctx->csr_s.as<uint2>() + pb[q], ctx->csr_pad.as<uint2>() + (size_t)q * M,
                                        (size_t)(pb[q + 1] - pb[q]) * 8, cudaMemcpyDeviceToDevice, st));
         }
-        if (ctx->timing) CK(cudaEventRecord(ev[EV_GATE], st));
+        if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_GATE], st));
 
         // ---- per-child normaliser ------------------------------------------------------------------
         nvtx.next("S3 sumLw");
@@ -914,7 +920,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             k_segsum<<<blocks_for(P, 256), 256, 0, st>>>(ctx->sk.as<uint32_t>(), ctx->sv.as<float>(), P, d_sumlw);
             CK(cudaGetLastError()); ctx->n_launches++;
         }
-        if (ctx->timing) CK(cudaEventRecord(ev[EV_SUMLW], st));
+        if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_SUMLW], st));
         CKR(orphan_stage());
 
         // ---- S4 moments -------------------------------------------------------------------------------
@@ -1000,14 +1006,14 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         }
     } else {
         CKR(join1());
-        if (ctx->timing) {
+        if (ctx->timing == 1) {
             CK(cudaEventRecord(ev[EV_GRID], st));
             CK(cudaEventRecord(ev[EV_GATE], st));
             CK(cudaEventRecord(ev[EV_SUMLW], st));
         }
         CKR(orphan_stage());
     }
-    if (ctx->timing) CK(cudaEventRecord(ev[EV_MOM], st));
+    if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_MOM], st));
 
     // ---- S5 filter ---------------------------------------------------------------------------------------
     nvtx.next("S5 finish");
@@ -1019,11 +1025,28 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
                                                          RAD_N.as<float>(), SAFE_N.as<uint8_t>(), PFLAG_N.as<uint32_t>(),
                                                          pool_cap_used ? (unsigned long long)pool_cap_used : ~0ull, d_ctl);
     CK(cudaGetLastError()); ctx->n_launches++;
-    pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev);
+    const unsigned seq_val = ctx->seq_next++;
+    pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev, ctx->h_seq_dev, seq_val);
     CK(cudaGetLastError());
     if (ctx->timing) CK(cudaEventRecord(ev[EV_END], st));
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-    CK(cudaStreamSynchronize(st));                                      // sync C
+    // sync C: the one host wait of a level.  Polling the mapped word k_publish writes last returns a few microseconds
+    // after the kernel; a stream synchronisation costs the GPU ~10 us of idle per level more.  The stream is queried
+    // now and then so that a failed launch cannot leave the loop spinning.
+    if (ctx->poll_sync) {
+        volatile unsigned* seq = ctx->h_seq;
+        for (unsigned spins = 0; *seq != seq_val; ++spins) {
+            if ((spins & 0x3fffu) == 0x3fffu) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q == cudaErrorNotReady) continue;
+                CK(q);
+                if (*seq != seq_val) CK(cudaStreamSynchronize(st));
+                break;
+            }
+        }
+    } else {
+        CK(cudaStreamSynchronize(st));
+    }
     memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
     if (have_pairs) {
         // fast flow: the pair / chunk counts arrive only now (in the other flows this re-reads known values)
@@ -1108,7 +1131,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         nx.max_radius_bits = hc.nx_max_radius_bits; nx.n_radius = hc.nx_n_radius; nx.n_parents = hc.nx_n_parents;
         nx.n_certified = hc.nx_n_certified; nx.sum_radius_fx = hc.nx_sum_radius_fx; nx.n_uncert = hc.nx_n_uncert;
     }
-    S.timed = ctx->timing; S.timed_pairs = have_pairs;
+    S.timed = ctx->timing; S.timed_pairs = have_pairs; S.ms_read = !ctx->timing;
 
     if (ctx->keep_pairs) {
         StepPairs& K = ctx->pairs[l];
@@ -1221,7 +1244,9 @@ hem_ctx* hem_create(int device, uint64_t seed)
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_ctl, sizeof(Ctl), cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void**)&ctx->h_ctl_dev, ctx->h_ctl, 0) != cudaSuccess) {
+        cudaHostGetDevicePointer((void**)&ctx->h_ctl_dev, ctx->h_ctl, 0) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_seq, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->h_seq_dev, ctx->h_seq, 0) != cudaSuccess) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
         return nullptr;
@@ -1235,6 +1260,8 @@ hem_ctx* hem_create(int device, uint64_t seed)
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* cs = getenv("HEM_OVERLAP")) ctx->overlap = atoi(cs) != 0;
+    if (const char* cs = getenv("HEM_POLL_SYNC")) ctx->poll_sync = atoi(cs) != 0;
+    *ctx->h_seq = 0u;
     if (const char* cs = getenv("HEM_HEAVY_ROWS")) ctx->heavy_rows = atoi(cs);
     if (const char* cs = getenv("HEM_HEAVY_REL")) ctx->heavy_rows_rel = atof(cs);
     cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming);
@@ -1266,6 +1293,7 @@ void hem_destroy(hem_ctx* ctx)
     for (DevBuf* b : all) release(*b);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->h_seq) cudaFreeHost(ctx->h_seq);
     if (ctx->h_icp) cudaFreeHost(ctx->h_icp);
     for (cudaEvent_t e : { ctx->ev_icp0, ctx->ev_icp1 }) if (e) cudaEventDestroy(e);
     for (auto& set : ctx->evs) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
@@ -1293,12 +1321,13 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
 {
     if (!ctx || !name) return HEM_ERR_INVALID;
     std::string k(name);
-    if (k == "timing") ctx->timing = value != 0;
+    if (k == "timing") ctx->timing = value == 2 ? 2 : (value != 0 ? 1 : 0);
     else if (k == "keep_pairs") ctx->keep_pairs = value != 0;
     else if (k == "smd_prefilter") ctx->smd_prefilter = value != 0;
     else if (k == "tight_box") ctx->tight_box = value != 0;
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "overlap") ctx->overlap = value != 0;
+    else if (k == "poll_sync") ctx->poll_sync = value != 0;
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "shard_upload") ctx->shard_upload = value != 0;
@@ -1441,20 +1470,6 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
     if (ctx->shx_pending) { CK(cudaStreamSynchronize(ctx->xchg_stream)); ctx->shx_pending = false; }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
-    for (uint32_t l = 0; l < cluster_level && l < ctx->evs.size(); ++l) {      // stage times of every step, read once
-        StepStats& S = ctx->stats[l];
-        if (!S.timed || ctx->evs[l].empty() || S.n_in == 0) continue;
-        cudaEvent_t* ev = ctx->evs[l].data();
-        float ms = 0;
-        const int pairs[7][2] = { { EV_BEGIN, EV_END }, { EV_BEGIN, EV_PREP }, { EV_PREP, EV_GRID }, { EV_GRID, EV_GATE },
-                                  { EV_GATE, EV_SUMLW }, { EV_SUMLW, EV_MOM }, { EV_MOM, EV_END } };
-        for (int k = 0; k < 7; ++k)
-            if (cudaEventElapsedTime(&ms, ev[pairs[k][0]], ev[pairs[k][1]]) == cudaSuccess) S.ms[k] = ms; else cudaGetLastError();
-        if (S.timed_pairs) {
-            if (cudaEventElapsedTime(&ms, ev[EV_GK0], ev[EV_GK1]) == cudaSuccess) S.ms[7] = ms; else cudaGetLastError();
-            if (cudaEventElapsedTime(&ms, ev[EV_MK0], ev[EV_MK1]) == cudaSuccess) S.ms[8] = ms; else cudaGetLastError();
-        }
-    }
     if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }
     return HEM_OK;
 }
@@ -1564,9 +1579,31 @@ int hem_clear_outputs(hem_ctx* ctx)
     return HEM_OK;
 }
 
+// Event times of a step, read on the first request after its build (a cudaEventElapsedTime costs ~3 us: reading all
+// of them at the end of every build was 0.23 ms of an 8-level pyramid).  The build has synchronised its streams.
+static void read_step_times(hem_ctx* ctx, int l)
+{
+    StepStats& S = ctx->stats[l];
+    if (S.ms_read) return;
+    S.ms_read = true;
+    if (!S.timed || (size_t)l >= ctx->evs.size() || ctx->evs[l].empty() || S.n_in == 0) return;
+    cudaSetDevice(ctx->device);
+    cudaEvent_t* ev = ctx->evs[l].data();
+    float ms = 0;
+    const int pairs[7][2] = { { EV_BEGIN, EV_END }, { EV_BEGIN, EV_PREP }, { EV_PREP, EV_GRID }, { EV_GRID, EV_GATE },
+                              { EV_GATE, EV_SUMLW }, { EV_SUMLW, EV_MOM }, { EV_MOM, EV_END } };
+    for (int k = 0; k < (S.timed == 1 ? 7 : 1); ++k)
+        if (cudaEventElapsedTime(&ms, ev[pairs[k][0]], ev[pairs[k][1]]) == cudaSuccess) S.ms[k] = ms; else cudaGetLastError();
+    if (S.timed_pairs) {
+        if (cudaEventElapsedTime(&ms, ev[EV_GK0], ev[EV_GK1]) == cudaSuccess) S.ms[7] = ms; else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, ev[EV_MK0], ev[EV_MK1]) == cudaSuccess) S.ms[8] = ms; else cudaGetLastError();
+    }
+}
+
 int hem_step_stats(const hem_ctx* ctx, int step, double* out)
 {
     if (!ctx || !out || step < 0 || step >= (int)ctx->stats.size()) return HEM_ERR_INVALID;
+    read_step_times(const_cast<hem_ctx*>(ctx), step);
     const StepStats& S = ctx->stats[step];
     out[0] = (double)S.n_in; out[1] = (double)S.n_parents; out[2] = (double)S.n_pairs; out[3] = (double)S.n_orphans;
     out[4] = (double)S.n_dropped; out[5] = (double)S.n_out; out[6] = (double)S.grid_cells; out[7] = S.cell_size;

@@ -88,12 +88,20 @@ struct Ctl {
 
 // Control block -> mapped pinned host memory.  The host reads step sizes after a stream sync; a DMA
 // readback would queue behind the bulk level downloads that share the D2H copy engine.
-__global__ void k_publish(const Ctl* __restrict__ d, Ctl* __restrict__ h_mapped)
+// `seq` (optional, mapped as well) receives `seq_val` once the block is visible to the host: the host may poll it
+// instead of paying a stream synchronisation (one block only).
+__global__ void k_publish(const Ctl* __restrict__ d, Ctl* __restrict__ h_mapped, unsigned* __restrict__ seq = nullptr,
+                          unsigned seq_val = 0u)
 {
     pdl_enter();
     const unsigned* s = reinterpret_cast<const unsigned*>(d);
     unsigned* o = reinterpret_cast<unsigned*>(h_mapped);
     for (unsigned i = threadIdx.x; i < sizeof(Ctl) / 4; i += blockDim.x) o[i] = s[i];
+    if (seq) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(seq) = seq_val;
+    }
 }
 
 // zero-fill by a kernel (a cudaMemsetAsync may be routed through a copy engine and queue behind bulk DMA)

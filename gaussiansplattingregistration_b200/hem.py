@@ -399,6 +399,17 @@ class HemContext:
             d[k] = int(d[k])
         return d
 
+    def step_stats_table(self, steps: int):
+        """hem_step_stats of steps 0..steps-1 as one float64 array [steps, len(STAT_NAMES)] (columns in STAT_NAMES order):
+        the cheap form for callers that read the statistics after every build."""
+        import numpy as np
+        out = np.empty((steps, _capi.STEP_STATS_LEN), dtype=np.float64)
+        row = C.POINTER(C.c_double)
+        base = out.ctypes.data
+        for l in range(steps):
+            self._check(self._lib.hem_step_stats(self._h, l, C.cast(base + l * out.strides[0], row)))
+        return out
+
     def info(self, name: str) -> float:
         out = C.c_double(0)
         self._check(self._lib.hem_get_info(self._h, name.encode(), C.byref(out)))

@@ -56,7 +56,10 @@ const char* hem_last_error(const hem_ctx* ctx);
 int hem_set_stream(hem_ctx* ctx, void* stream);
 
 /* Options (all optional):
- *   "timing"      1 -> record CUDA events around every stage (hem_step_stats ms fields)
+ *   "timing"      1 -> record CUDA events around every stage (hem_step_stats ms fields);
+ *                 2 -> only around each level and its two hot kernels (ms_total, ms_k_gate,
+ *                 ms_k_moments; the other ms fields stay 0).  The event times are read on the
+ *                 first hem_step_stats of a step after its build, not by the build itself.
  *   "keep_pairs"  1 -> retain each step's (parent, child, wL) lists for hem_step_pairs
  *   "cell_scale"  grid cell = cell_scale * geometric-mean parent radius (default 0.55)
  *   "smd_prefilter" 1 (default) -> certified Mahalanobis pre-test inside the KLD gate (same
