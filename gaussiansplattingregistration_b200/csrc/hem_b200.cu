@@ -452,6 +452,26 @@ int robust_box(hem_ctx* ctx, const float4* geo, int64_t n, const float bmin[3], 
 // ---------------------------------------------------------------------------
 // one clustering step: levels[l] -> levels[l+1]
 // ---------------------------------------------------------------------------
+
+// Host wait for the control block of a step: poll the mapped word k_publish writes last (returns a few microseconds
+// after the kernel; a stream synchronisation costs the GPU ~6 us of idle more).  The stream is queried now and then so
+// that a failed launch cannot leave the loop spinning.
+static int wait_publish(hem_ctx* ctx, cudaStream_t st, unsigned seq_val)
+{
+    if (!ctx->poll_sync) { CK(cudaStreamSynchronize(st)); return HEM_OK; }
+    volatile unsigned* seq = ctx->h_seq;
+    for (unsigned spins = 0; *seq != seq_val; ++spins) {
+        if ((spins & 0x3fffu) == 0x3fffu) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaErrorNotReady) continue;
+            CK(q);
+            if (*seq != seq_val) CK(cudaStreamSynchronize(st));
+            break;
+        }
+    }
+    return HEM_OK;
+}
+
 int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, float color_delta, float decay_rate,
              uint64_t rng_base)
 {
@@ -537,9 +557,10 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         pdl(k_prep, (unsigned)std::min<int64_t>(blocks_for(n, 256), (int64_t)ctx->sm_count * 4), 256, 0, st)(
             geo, n, distance_delta, RAD.as<float>(), PFLAG.as<uint32_t>(), SAFE.as<uint8_t>(), d_ctl);
         CK(cudaGetLastError()); ctx->n_launches++;
-        pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev, (unsigned*)nullptr, 0u);
+        const unsigned seq_a = ctx->seq_next++;
+        pdl(k_publish, 1, 32, 0, st)(d_ctl, ctx->h_ctl_dev, ctx->h_seq_dev, seq_a);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));                                  // sync A (level 0 / after an erasing filter only)
+        CKR(wait_publish(ctx, st, seq_a));                              // sync A (level 0 / after an erasing filter only)
         ps = *ctx->h_ctl;
     }
     ctx->prep_valid = false;
@@ -1030,23 +1051,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     CK(cudaGetLastError());
     if (ctx->timing) CK(cudaEventRecord(ev[EV_END], st));
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-    // sync C: the one host wait of a level.  Polling the mapped word k_publish writes last returns a few microseconds
-    // after the kernel; a stream synchronisation costs the GPU ~10 us of idle per level more.  The stream is queried
-    // now and then so that a failed launch cannot leave the loop spinning.
-    if (ctx->poll_sync) {
-        volatile unsigned* seq = ctx->h_seq;
-        for (unsigned spins = 0; *seq != seq_val; ++spins) {
-            if ((spins & 0x3fffu) == 0x3fffu) {
-                const cudaError_t q = cudaStreamQuery(st);
-                if (q == cudaErrorNotReady) continue;
-                CK(q);
-                if (*seq != seq_val) CK(cudaStreamSynchronize(st));
-                break;
-            }
-        }
-    } else {
-        CK(cudaStreamSynchronize(st));
-    }
+    CKR(wait_publish(ctx, st, seq_val));                                // sync C: the one host wait of a level
     memcpy(ctx->h_counters, ctx->h_ctl->counters, C_COUNT * sizeof(unsigned long long));
     if (have_pairs) {
         // fast flow: the pair / chunk counts arrive only now (in the other flows this re-reads known values)
