@@ -152,6 +152,16 @@ struct hem_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_geo = nullptr, ev_sh = nullptr, ev_level = nullptr;
     bool sh_pending = false;                     // level-0 SH H2D still in flight on copy_stream
+    // Geometry-first pipeline (host SH rows, one GPU): while the level-0 SH rows are still crossing PCIe, a step produces
+    // the geometry rows of its output level only and stashes what the SH pass needs (pairs, offsets, parent table,
+    // normalisers, orphan ranks); the SH passes run level by level once the rows have landed (sh_catch_up).
+    struct ShStash { DevBuf csr, off, ptab, sumlw, orank; int64_t n = 0, np = 0, P = 0; };
+    std::vector<ShStash> stash;
+    DevBuf sh_ctl;                               // ticket counters of the SH passes
+    int geo_first = 1;                           // option "geo_first": 0 off, 1 while the upload is in flight, 2 every level of a host-SH build (tests)
+    int sh_level = 0;                            // levels 0..sh_level of this build have their SH rows
+    bool bind_too_small = false;                 // a bound output buffer was smaller than its level (reported by the build)
+    cudaStream_t d2h_stream = nullptr;           // bound outputs leave here (the SH upload owns copy_stream)
     int64_t sh_gather_chunk = 0;                 // > 0: only this rank's slice of the SH rows was uploaded; all-gather after the wait
     float* sh_gather_buf = nullptr;
     int sh_gather_row = 0;
@@ -453,6 +463,102 @@ int robust_box(hem_ctx* ctx, const float4* geo, int64_t n, const float bmin[3], 
 // one clustering step: levels[l] -> levels[l+1]
 // ---------------------------------------------------------------------------
 
+// A bound output level leaves for the caller's buffers: the geometry arrays are de-interleaved by a kernel on the MAIN
+// stream (the persistent gate / moment kernels of the next level would starve it elsewhere), the DMA runs on the
+// download stream (the level-0 SH upload owns the copy stream; PCIe carries both directions at once).
+// `do_geo` / `do_sh`: which half of the level to send (the geometry-first pipeline sends them at different times).
+static int send_level(hem_ctx* ctx, size_t lv, bool do_geo, bool do_sh, bool* too_small)
+{
+    if (lv >= ctx->binds.size() || !ctx->binds[lv].set) return HEM_OK;
+    cudaStream_t st = ctx->stream;
+    const hem_ctx::OutBind& B = ctx->binds[lv];
+    if (B.cap < ctx->levels[lv].n) { *too_small = true; return HEM_OK; }
+    Level& LV = ctx->levels[lv];
+    const int64_t m = LV.n;
+    if (m <= 0) return HEM_OK;
+    const bool hx = B.xyz && !is_device_ptr(B.xyz), hc = B.color && !is_device_ptr(B.color);
+    const bool ho = B.opacity && !is_device_ptr(B.opacity), hv = B.cov6 && !is_device_ptr(B.cov6);
+    float *dx = nullptr, *dc = nullptr, *dop = nullptr, *dcv = nullptr;
+    if (do_geo) {
+        if (hx) CKR(ensure(ctx, LV.ex_xyz, (size_t)m * 12));
+        if (hc) CKR(ensure(ctx, LV.ex_col, (size_t)m * 12));
+        if (ho) CKR(ensure(ctx, LV.ex_op, (size_t)m * 4));
+        if (hv) CKR(ensure(ctx, LV.ex_cov, (size_t)m * 24));
+        dx = B.xyz ? (hx ? LV.ex_xyz.as<float>() : B.xyz) : nullptr;
+        dc = B.color ? (hc ? LV.ex_col.as<float>() : B.color) : nullptr;
+        dop = B.opacity ? (ho ? LV.ex_op.as<float>() : B.opacity) : nullptr;
+        dcv = B.cov6 ? (hv ? LV.ex_cov.as<float>() : B.cov6) : nullptr;
+        if (dx || dc || dop || dcv) {
+            k_export<<<blocks_for(m, 256), 256, 0, st>>>(LV.geo.as<float4>(), m, dx, dc, dop, dcv, nullptr, nullptr);
+            CK(cudaGetLastError()); ctx->n_launches++;
+        }
+    }
+    cudaStream_t cs = ctx->d2h_stream;
+    CK(cudaEventRecord(ctx->ev_level, st));
+    CK(cudaStreamWaitEvent(cs, ctx->ev_level, 0));
+    if (do_sh && ctx->shx_pending) CK(cudaStreamWaitEvent(cs, ctx->ev_shx, 0));      // SH rows still in the exchange
+    if (do_sh && B.sh && ctx->F > 0) {
+        const bool to_dev = is_device_ptr(B.sh);
+        CK(cudaMemcpyAsync(B.sh, LV.shp, (size_t)m * ctx->F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
+        if (!to_dev) ctx->bytes_d2h += (size_t)m * ctx->F * 4;
+    }
+    if (do_geo) {
+        if (hv) { CK(cudaMemcpyAsync(B.cov6, dcv, (size_t)m * 24, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 24; }
+        if (hx) { CK(cudaMemcpyAsync(B.xyz, dx, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
+        if (hc) { CK(cudaMemcpyAsync(B.color, dc, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
+        if (ho) { CK(cudaMemcpyAsync(B.opacity, dop, (size_t)m * 4, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 4; }
+    }
+    return HEM_OK;
+}
+
+// SH rows of level l + 1 from the stash of step l (geometry-first pipeline): the moment kernel's SH half over the
+// step's pairs, then the orphans' rows.  Level l's SH rows must be in place (wait_sh / the previous pass).
+static int sh_pass(hem_ctx* ctx, int l)
+{
+    cudaStream_t st = ctx->stream;
+    if ((size_t)l >= ctx->stash.size()) return HEM_OK;          // an empty level: nothing was stashed
+    const hem_ctx::ShStash& H = ctx->stash[l];
+    Level& in = ctx->levels[l];
+    Level& out = ctx->levels[l + 1];
+    const int Fp = ctx->Fp;
+    if (ctx->sh_pending) CKR(wait_sh(ctx));
+    if (H.n <= 0) return HEM_OK;
+    NvtxRange nvtx("hem.sh_pass");
+    CKR(ensure(ctx, ctx->sh_ctl, sizeof(Ctl)));
+    CK(cudaMemsetAsync(ctx->sh_ctl.p, 0, sizeof(Ctl), st));
+    Ctl* c = ctx->sh_ctl.as<Ctl>();
+    if (H.np > 0 && H.P > 0) {
+        MomArgs M;
+        M.geo = in.geo.as<float4>(); M.sh = in.shp; M.Fp = Fp; M.ptab = H.ptab.as<uint2>(); M.pair_off_s = H.off.as<uint32_t>();
+        M.csr_s = H.csr.as<uint2>(); M.sumlw = H.sumlw.as<float>();
+        M.t_begin = 0; M.t_end = (int)H.np;
+        M.counters = c->counters;
+        M.pool_cap = ~0ull;
+        M.hv_flag = nullptr; M.hv_done = nullptr; M.n_heavy = &c->n_heavy; M.heavy_thr = 0u;
+        M.by_rank = 1; M.ogeo = out.geo.as<float4>(); M.osh = out.sh.as<float>();
+        const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((H.np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
+        if (Fp <= 64) k_moments<2, false, 2><<<mgrid, MOM_WARPS * 32, 0, st>>>(M);
+        else if (Fp <= 128) k_moments<4, false, 2><<<mgrid, MOM_WARPS * 32, 0, st>>>(M);
+        else k_moments<8, false, 2><<<mgrid, MOM_WARPS * 32, 0, st>>>(M);
+        CK(cudaGetLastError()); ctx->n_launches++;
+    }
+    k_orphans<<<blocks_for(H.n, 256), 256, 0, st>>>(in.geo.as<float4>(), in.shp, Fp, H.n, H.sumlw.as<float>(), H.orank.as<uint32_t>(),
+                                                    (uint32_t)H.np, out.geo.as<float4>(), out.sh.as<float>(), 0, 1);
+    CK(cudaGetLastError()); ctx->n_launches++;
+    return HEM_OK;
+}
+
+// run the SH passes of the stashed steps sh_level .. upto - 1 and send the bound SH outputs of their levels
+static int sh_catch_up(hem_ctx* ctx, int upto, bool* too_small)
+{
+    for (int l = ctx->sh_level; l < upto; ++l) {
+        CKR(sh_pass(ctx, l));
+        ctx->sh_level = l + 1;
+        CKR(send_level(ctx, (size_t)l + 1, false, true, too_small));
+    }
+    return HEM_OK;
+}
+
 // Host wait for the control block of a step: poll the mapped word k_publish writes last (returns a few microseconds
 // after the kernel; a stream synchronisation costs the GPU ~6 us of idle more).  The stream is queried now and then so
 // that a failed launch cannot leave the loop spinning.
@@ -507,6 +613,24 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
 
     const float4* geo = in.geo.as<float4>();
     const float* sh = in.shp;
+
+    // Geometry-first (see hem_ctx::ShStash): as long as the level-0 SH rows are still crossing PCIe, this step makes the
+    // geometry rows of its output level only.  Once they have landed, the stashed steps get their SH passes and the
+    // build goes on with fused steps.
+    bool defer_sh = false;
+    {
+        bool in_flight = false;
+        if (ctx->sh_pending && ctx->sh_gather_chunk == 0) {
+            const cudaError_t q = cudaEventQuery(ctx->ev_sh);
+            if (q == cudaErrorNotReady || ctx->geo_first == 2) in_flight = true; else CK(q);
+        }
+        defer_sh = ctx->geo_first && in_flight && ctx->world == 1 && Fp > 0 && !ctx->keep_pairs && !ctx->heavy_hint;
+        if (!defer_sh && ctx->sh_level < l) {
+            bool small = false;
+            CKR(sh_catch_up(ctx, l, &small));
+            if (small) ctx->bind_too_small = true;
+        }
+    }
 
     // ---- S1 prep --------------------------------------------------------------------------
     // control block + the arrays that must start from zero live in one allocation: one memset per step
@@ -609,8 +733,8 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         if (fork2) {
             CK(cudaEventRecord(ctx->ev_fork, st));
             CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-            if (ctx->sh_pending) CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_sh, 0));    // level-0 SH rows still arriving
-        } else if (ctx->sh_pending) {
+            if (ctx->sh_pending && !defer_sh) CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_sh, 0));    // level-0 SH rows still arriving
+        } else if (ctx->sh_pending && !defer_sh) {
             CKR(wait_sh(ctx));
         }
         CKR(cub_call(ctx, fork2 ? ctx->cubtmp2 : ctx->cubtmp, [&](void* t, size_t& b) {
@@ -618,7 +742,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             return cub::DeviceScan::ExclusiveSum(t, b, it, ctx->orank.as<uint32_t>(), (int)n, s2);
         }));
         pdl(k_orphans, blocks_for(n, 256), 256, 0, s2)(geo, sh, Fp, n, d_sumlw, ctx->orank.as<uint32_t>(),
-                                                       (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>());
+                                                       (uint32_t)np, out.geo.as<float4>(), out.sh.as<float>(), 1, defer_sh ? 0 : 1);
         CK(cudaGetLastError()); ctx->n_launches++;
         if (fork2) CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
         return HEM_OK;
@@ -963,7 +1087,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             CKR(ensure(ctx, ctx->stage_sh, (size_t)slab_chunk(np, G) * G * std::max(Fp, 1) * 4));
             M.by_rank = 0; M.ogeo = ctx->stage_geo.as<float4>(); M.osh = ctx->stage_sh.as<float>();
         }
-        if (ctx->sh_pending) CKR(wait_sh(ctx));
+        if (ctx->sh_pending && !defer_sh) CKR(wait_sh(ctx));
         if (ctx->timing) CK(cudaEventRecord(ev[EV_MK0], st));
         if (my_np > 0) {
             const unsigned mgrid = (unsigned)std::min<int64_t>(blocks_for((my_np + MOM_B - 1) / MOM_B, MOM_WARPS), (int64_t)ctx->sm_count * 4);
@@ -972,7 +1096,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             // step that meets the first one is redone, like a pool overflow).  Sharded runs keep the ordinary kernel:
             // a redo decided by one rank alone would take the ranks out of step (not validated on several GPUs yet).
             launched_heavy = ctx->heavy_pairs && ctx->heavy_hint && G == 1;
-            if (launched_heavy) {
+            if (defer_sh) {          // geometry rows only (never together with the heavy path: heavy_hint ends the deferral)
+                if (Fp <= 64) pdl(k_moments<2, false, 1>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else if (Fp <= 128) pdl(k_moments<4, false, 1>, mgrid, MOM_WARPS * 32, 0, st)(M);
+                else pdl(k_moments<8, false, 1>, mgrid, MOM_WARPS * 32, 0, st)(M);
+            } else if (launched_heavy) {
                 if (Fp <= 64) pdl(k_moments<2, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
                 else if (Fp <= 128) pdl(k_moments<4, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
                 else pdl(k_moments<8, true>, mgrid, MOM_WARPS * 32, 0, st)(M);
@@ -1102,6 +1230,33 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
     S.n_orphans = norph;
     S.n_dropped = ninvalid;
     out.n = npre;
+    if (defer_sh) {
+        // what the SH pass of this step needs, out of the buffers the next step reuses
+        if (ctx->stash.size() <= (size_t)l) ctx->stash.resize((size_t)l + 1);
+        hem_ctx::ShStash& H = ctx->stash[l];
+        H.n = n; H.np = have_pairs ? np : 0; H.P = have_pairs ? P : 0;
+        CKR(ensure(ctx, H.sumlw, (size_t)n * 4));
+        CKR(ensure(ctx, H.orank, (size_t)n * 4));
+        CK(cudaMemcpyAsync(H.sumlw.p, d_sumlw, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(H.orank.p, ctx->orank.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        if (H.np > 0 && H.P > 0) {
+            CKR(ensure(ctx, H.csr, (size_t)H.P * 8));
+            CKR(ensure(ctx, H.off, (size_t)(H.np + 1) * 4));
+            CKR(ensure(ctx, H.ptab, (size_t)H.np * 8));
+            CK(cudaMemcpyAsync(H.csr.p, ctx->csr_s.p, (size_t)H.P * 8, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(H.off.p, ctx->pair_off_s.p, (size_t)(H.np + 1) * 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(H.ptab.p, PTAB.p, (size_t)H.np * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (ninvalid > 0) {          // the filter below moves whole rows: bring the SH rows up to this level first
+            bool small = false;
+            CKR(sh_catch_up(ctx, l, &small));
+            if (small) ctx->bind_too_small = true;
+            CKR(sh_pass(ctx, l));    // (its bound output leaves after the filter, with the geometry)
+            ctx->sh_level = l + 1;
+        }
+    } else {
+        ctx->sh_level = l + 1;
+    }
     if (ninvalid > 0) {
         // rare path: erase invalid outputs keeping order (mixture.cpp:262-282)
         CKR(ensure(ctx, ctx->vflag, npre * 4));
@@ -1258,6 +1413,7 @@ hem_ctx* hem_create(int device, uint64_t seed)
     }
     ctx->stream = ctx->own_stream;
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->xchg_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_xfork, cudaEventDisableTiming);
@@ -1266,6 +1422,7 @@ hem_ctx* hem_create(int device, uint64_t seed)
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* cs = getenv("HEM_OVERLAP")) ctx->overlap = atoi(cs) != 0;
     if (const char* cs = getenv("HEM_POLL_SYNC")) ctx->poll_sync = atoi(cs) != 0;
+    if (const char* cs = getenv("HEM_GEO_FIRST")) ctx->geo_first = atoi(cs);
     *ctx->h_seq = 0u;
     if (const char* cs = getenv("HEM_HEAVY_ROWS")) ctx->heavy_rows = atoi(cs);
     if (const char* cs = getenv("HEM_HEAVY_REL")) ctx->heavy_rows_rel = atof(cs);
@@ -1303,6 +1460,9 @@ void hem_destroy(hem_ctx* ctx)
     for (cudaEvent_t e : { ctx->ev_icp0, ctx->ev_icp1 }) if (e) cudaEventDestroy(e);
     for (auto& set : ctx->evs) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
+    for (auto& h : ctx->stash) for (DevBuf* b : { &h.csr, &h.off, &h.ptab, &h.sumlw, &h.orank }) if (b->p) cudaFree(b->p);
+    if (ctx->sh_ctl.p) cudaFree(ctx->sh_ctl.p);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->xchg_stream) { cudaStreamSynchronize(ctx->xchg_stream); cudaStreamDestroy(ctx->xchg_stream); }
     for (cudaEvent_t e : { ctx->ev_xfork, ctx->ev_shx }) if (e) cudaEventDestroy(e);
@@ -1333,6 +1493,7 @@ int hem_set_option(hem_ctx* ctx, const char* name, double value)
     else if (k == "sumlw_mode") ctx->sumlw_mode = (int)value;
     else if (k == "overlap") ctx->overlap = value != 0;
     else if (k == "poll_sync") ctx->poll_sync = value != 0;
+    else if (k == "geo_first") ctx->geo_first = value == 2 ? 2 : (value != 0 ? 1 : 0);
     else if (k == "shard_min_n") ctx->shard_min_n = (int64_t)value;
     else if (k == "box_quantile") { if (!(value >= 0 && value < 0.5)) { ctx->err = "box_quantile must be in [0, 0.5)"; return HEM_ERR_INVALID; } ctx->box_q = value; }
     else if (k == "shard_upload") ctx->shard_upload = value != 0;
@@ -1427,54 +1588,22 @@ int hem_build_pyramid(hem_ctx* ctx, const float* xyz, const float* color, const 
         }
     }
     uint64_t base = ctx->rng_base_set ? ctx->rng_base : (uint64_t)n;
-    bool bind_too_small = false;
+    ctx->bind_too_small = false;
+    ctx->sh_level = 0;
+    for (auto& h : ctx->stash) h.n = h.np = h.P = 0;
     for (uint32_t l = 0; l < cluster_level; ++l) {
         CKR(run_step(ctx, (int)l, hem_reduction, distance_delta, color_delta, decay_rate, base));
         base += (uint64_t)(ctx->stats[l].n_parents + ctx->stats[l].n_orphans);    // pre-filter size, mixture.cpp:257-259
-        // a bound output leaves on the copy stream while the next level is being built
-        const size_t lv = (size_t)l + 1;
-        if (lv < ctx->binds.size() && ctx->binds[lv].set) {
-            const hem_ctx::OutBind& B = ctx->binds[lv];
-            if (B.cap < ctx->levels[lv].n) { bind_too_small = true; continue; }
-            // The de-interleave kernel runs on the MAIN stream (the persistent gate / moment kernels of the
-            // next level would starve it on the copy stream); the copy stream then carries DMA only.
-            Level& LV = ctx->levels[lv];
-            const int64_t m = LV.n;
-            if (m > 0) {
-                const bool hx = B.xyz && !is_device_ptr(B.xyz), hc = B.color && !is_device_ptr(B.color);
-                const bool ho = B.opacity && !is_device_ptr(B.opacity), hv = B.cov6 && !is_device_ptr(B.cov6);
-                if (hx) CKR(ensure(ctx, LV.ex_xyz, (size_t)m * 12));
-                if (hc) CKR(ensure(ctx, LV.ex_col, (size_t)m * 12));
-                if (ho) CKR(ensure(ctx, LV.ex_op, (size_t)m * 4));
-                if (hv) CKR(ensure(ctx, LV.ex_cov, (size_t)m * 24));
-                float* dx = B.xyz ? (hx ? LV.ex_xyz.as<float>() : B.xyz) : nullptr;
-                float* dc = B.color ? (hc ? LV.ex_col.as<float>() : B.color) : nullptr;
-                float* dop = B.opacity ? (ho ? LV.ex_op.as<float>() : B.opacity) : nullptr;
-                float* dcv = B.cov6 ? (hv ? LV.ex_cov.as<float>() : B.cov6) : nullptr;
-                if (dx || dc || dop || dcv) {
-                    k_export<<<blocks_for(m, 256), 256, 0, st>>>(LV.geo.as<float4>(), m, dx, dc, dop, dcv, nullptr, nullptr);
-                    CK(cudaGetLastError()); ctx->n_launches++;
-                }
-                CK(cudaEventRecord(ctx->ev_level, st));
-                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_level, 0));
-                if (ctx->shx_pending) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_shx, 0));      // SH rows still in the exchange
-                cudaStream_t cs = ctx->copy_stream;
-                if (B.sh && ctx->F > 0) {
-                    const bool to_dev = is_device_ptr(B.sh);
-                    CK(cudaMemcpyAsync(B.sh, LV.shp, (size_t)m * ctx->F * 4, to_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
-                    if (!to_dev) ctx->bytes_d2h += (size_t)m * ctx->F * 4;
-                }
-                if (hv) { CK(cudaMemcpyAsync(B.cov6, dcv, (size_t)m * 24, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 24; }
-                if (hx) { CK(cudaMemcpyAsync(B.xyz, dx, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
-                if (hc) { CK(cudaMemcpyAsync(B.color, dc, (size_t)m * 12, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 12; }
-                if (ho) { CK(cudaMemcpyAsync(B.opacity, dop, (size_t)m * 4, cudaMemcpyDeviceToHost, cs)); ctx->bytes_d2h += (size_t)m * 4; }
-            }
-        }
+        // a bound output leaves while the next level is being built (its SH rows later, if the step left them to the SH pass)
+        CKR(send_level(ctx, (size_t)l + 1, true, ctx->sh_level >= (int)l + 1, &ctx->bind_too_small));
     }
+    CKR(sh_catch_up(ctx, (int)cluster_level, &ctx->bind_too_small));
+    const bool bind_too_small = ctx->bind_too_small;
     if (ctx->sh_pending) CKR(wait_sh(ctx));
     if (ctx->shx_pending) { CK(cudaStreamSynchronize(ctx->xchg_stream)); ctx->shx_pending = false; }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
     if (bind_too_small) { ctx->err = "a bound output buffer is smaller than its level (use hem_level_size + hem_level_copy)"; return HEM_ERR_INVALID; }
     return HEM_OK;
 }

@@ -1361,10 +1361,15 @@ constexpr uint32_t HEAVY_CHUNK = 2048;    // pairs per work item of the heavy ke
 // NSH = SH accumulators per lane: rows of up to 32*NSH floats (2 covers SH degree <= 3, the 3DGS standard)
 // DEFER = false: the ordinary kernel; it only reports that a heavy parent exists (the host then redoes the step
 // with DEFER = true, which leaves the tickets of heavy parents to k_moments_heavy).
-template <int NSH, bool DEFER>
+// PART: 0 = geometry and SH rows in one pass (the resident path), 1 = geometry rows only, 2 = SH rows only.  The split
+// passes serve the geometry-first pipeline of a build whose SH rows are still on their way from the host: every level's
+// gates, claims and geometry moments need the 64-byte geometry rows only; the SH pass replays the pairs afterwards.
+// Both passes add in the fused pass's order, so the rows are bit-identical to it.
+template <int NSH, bool DEFER, int PART = 0>
 __global__ void __launch_bounds__(MOM_WARPS * 32, HEM_MOM_MINB)
 k_moments(MomArgs A)
 {
+    constexpr bool DO_GEO = PART != 2, DO_SH = PART != 1;
     pdl_enter();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1432,11 +1437,13 @@ k_moments(MomArgs A)
             if (j == 3) outv = w_s;
             if (j == 11 || j == 15) outv = 0.0f;      // det and parent flag are filled in by k_finish
             const size_t orow_i = A.by_rank ? (size_t)srank : (size_t)(tb + cur);
-            if (lane < 16) ogeof[16 * orow_i + lane] = outv;
-            float* orow = A.osh + orow_i * Fp;
+            if (DO_GEO && lane < 16) ogeof[16 * orow_i + lane] = outv;
+            if (DO_SH) {
+                float* orow = A.osh + orow_i * Fp;
 #pragma unroll
-            for (int q = 0; q < NSH; ++q)
-                if (lane + 32 * q < Fp) orow[lane + 32 * q] = fm(inv_w, shacc[q]);
+                for (int q = 0; q < NSH; ++q)
+                    if (lane + 32 * q < Fp) orow[lane + 32 * q] = fm(inv_w, shacc[q]);
+            }
         };
         auto advance = [&]() {
             finalize();
@@ -1472,23 +1479,31 @@ k_moments(MomArgs A)
                     const int c = min(g + u, cnt - 1);
                     const uint32_t cc = __shfl_sync(full, ch, c);
                     wc[u] = __shfl_sync(full, w, c);
-                    gv[u] = geof[16 * (size_t)cc + j];
-                    const float* row = A.sh + (size_t)cc * Fp;
+                    gv[u] = DO_GEO ? geof[16 * (size_t)cc + j] : 0.0f;
+                    if (DO_SH) {
+                        const float* row = A.sh + (size_t)cc * Fp;
 #pragma unroll
-                    for (int q = 0; q < NSH; ++q) vs[q][u] = lane + 32 * q < Fp ? row[lane + 32 * q] : 0.0f;
+                        for (int q = 0; q < NSH; ++q) vs[q][u] = lane + 32 * q < Fp ? row[lane + 32 * q] : 0.0f;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < MOM_U; ++u) {
                     if (g + u < cnt) {                                  // uniform
                         while (k0 + g + u == nextb && cur < nb - 1) advance();   // parent boundary (empty parents too)
-                        const float dv = fs(gv[u], pmj);
-                        const float da = __shfl_sync(full, dv, sa), db = __shfl_sync(full, dv, sb);
-                        // tolerance-class sums (the reference's own summation order is not reproducible,
-                        // DESIGN.md §2): fused multiply-adds
-                        const float val = (j == 3) ? 1.0f : (is_cov ? fmaf(da, db, gv[u]) : gv[u]);
-                        accg = fmaf(wc[u], val, accg);
+                        if (DO_GEO) {
+                            const float dv = fs(gv[u], pmj);
+                            const float da = __shfl_sync(full, dv, sa), db = __shfl_sync(full, dv, sb);
+                            // tolerance-class sums (the reference's own summation order is not reproducible,
+                            // DESIGN.md §2): fused multiply-adds
+                            const float val = (j == 3) ? 1.0f : (is_cov ? fmaf(da, db, gv[u]) : gv[u]);
+                            accg = fmaf(wc[u], val, accg);
+                        } else {
+                            accg = fmaf(wc[u], 1.0f, accg);       // the weight sum (lane 3 of the fused pass), on every lane
+                        }
+                        if (DO_SH) {
 #pragma unroll
-                        for (int q = 0; q < NSH; ++q) shacc[q] = fmaf(vs[q][u], wc[u], shacc[q]);
+                            for (int q = 0; q < NSH; ++q) shacc[q] = fmaf(vs[q][u], wc[u], shacc[q]);
+                        }
                     }
                 }
             }
@@ -1633,7 +1648,7 @@ struct IsOrphan {
 __global__ void __launch_bounds__(256)
 k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, int64_t n,
           const float* __restrict__ sumlw, const uint32_t* __restrict__ orank, uint32_t np,
-          float4* __restrict__ ogeo, float* __restrict__ osh)
+          float4* __restrict__ ogeo, float* __restrict__ osh, int do_geo, int do_sh)      // which half of a row to copy
 {
     pdl_enter();
     const unsigned full = 0xffffffffu;
@@ -1664,28 +1679,28 @@ k_orphans(const float4* __restrict__ geo, const float* __restrict__ sh, int Fp, 
             for (int u = 0; u < ORPH_U; ++u) {
                 if (srcs[u] < 0) continue;
                 const size_t ci = (size_t)(wbase + srcs[u]);
-                if (lane < 4) g[u] = geo[4 * ci + lane];
+                if (do_geo && lane < 4) g[u] = geo[4 * ci + lane];
                 const float* srow = sh + ci * Fp;
-                if (lane < Fp) a[u] = srow[lane];
-                if (lane + 32 < Fp) b[u] = srow[lane + 32];
+                if (do_sh && lane < Fp) a[u] = srow[lane];
+                if (do_sh && lane + 32 < Fp) b[u] = srow[lane + 32];
             }
 #pragma unroll
             for (int u = 0; u < ORPH_U; ++u) {
                 if (srcs[u] < 0) continue;
-                if (lane < 4) ogeo[4 * dsts[u] + lane] = g[u];
+                if (do_geo && lane < 4) ogeo[4 * dsts[u] + lane] = g[u];
                 float* drow = osh + dsts[u] * Fp;
-                if (lane < Fp) drow[lane] = a[u];
-                if (lane + 32 < Fp) drow[lane + 32] = b[u];
+                if (do_sh && lane < Fp) drow[lane] = a[u];
+                if (do_sh && lane + 32 < Fp) drow[lane + 32] = b[u];
             }
         } else {
 #pragma unroll
             for (int u = 0; u < ORPH_U; ++u) {
                 if (srcs[u] < 0) continue;
                 const size_t ci = (size_t)(wbase + srcs[u]);
-                if (lane < 4) ogeo[4 * dsts[u] + lane] = geo[4 * ci + lane];
+                if (do_geo && lane < 4) ogeo[4 * dsts[u] + lane] = geo[4 * ci + lane];
                 const float* srow = sh + ci * Fp;
                 float* drow = osh + dsts[u] * Fp;
-                for (int q = lane; q < Fp; q += 32) drow[q] = srow[q];
+                if (do_sh) for (int q = lane; q < Fp; q += 32) drow[q] = srow[q];
             }
         }
     }

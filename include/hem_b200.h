@@ -72,6 +72,12 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *   "overlap"     1 (default) -> stages of a step that do not depend on each other run side by side on a second stream
  *                 (control-block reset + parent-rank scan beside the grid build, orphan scan + copy beside the moment
  *                 kernel); 0 -> one chain.  Same results either way.
+ *   "geo_first"   1 (default) -> a build whose SH rows come from HOST memory produces, level after level, the geometry
+ *                 rows only for as long as the SH rows are still crossing PCIe (gates, claims and geometry moments need
+ *                 the 64-byte geometry rows alone), sends bound geometry outputs back meanwhile, and runs the SH passes
+ *                 of those levels once the rows have landed; 0 -> every step waits for the SH rows it reads; 2 -> defer
+ *                 on every level of such a build (tests).  Results are bit-identical in all three.
+ *   "poll_sync"   1 (default) -> the one host wait per level polls a mapped word instead of synchronising the stream
  *   "heavy_rows"  a parent whose search box has more rows of cells than max(heavy_rows, heavy_rows_rel x the box of a
  *                 parent of geometric-mean radius) is scanned by the whole grid in segments instead of by one warp
  *                 (defaults 128 and 16; heavy_rows = 0: never; single GPU)

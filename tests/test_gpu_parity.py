@@ -816,3 +816,43 @@ def test_gpu_round2_switches_do_not_change_results():
                 assert np.array_equal(a[k], b[k], equal_nan=True), (opts, l + 1, k)
         for k in ("parent_idx", "off", "child", "wl", "sumlw"):
             assert np.array_equal(pairs[k], ref_pairs[k]), (opts, k)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 0])
+def test_gpu_geometry_first_pipeline_is_bit_identical(mode):
+    """Host (pinned) inputs + bound host outputs: while the SH rows are still crossing PCIe the build produces geometry
+    rows only and replays the pairs for the SH rows afterwards (`geo_first`; 2 defers on every level).  Levels, bound
+    outputs and statistics equal those of a device-resident build bit for bit - also when the validity filter drops
+    rows in the middle of the deferred levels."""
+    import torch
+    from gaussiansplattingregistration_b200.hem import HemContext
+    c = synth(400_000, seed=91, density=5000.0)
+    arrs = [a.copy() for a in c.arrays()]
+    arrs[3][1000:1040] = 0.0            # singular covariances: det = 0 children, dropped by the filter if they end up alone
+    arrs[0][5000:5010] = np.nan         # NaN means: never in any radius -> orphans -> invalid rows
+    L = 4
+    with HemContext(0, seed=21) as ctx:
+        ctx.build(*[torch.from_numpy(a).cuda() for a in arrs], cluster_level=L)
+        want = [ctx.level(l, with_internal=True) for l in range(L + 1)]
+        dropped = [ctx.step_stats(l)["n_dropped"] for l in range(L)]
+    assert sum(dropped) > 0, "the cloud is meant to exercise the validity filter"
+    pinned = [torch.from_numpy(a).pin_memory() for a in arrs]
+    with HemContext(0, seed=21) as ctx:
+        ctx.set_option("geo_first", mode)
+        bufs = {}
+        for l in range(1, L + 1):
+            cap = c.n
+            bufs[l] = [torch.empty((cap, 3)).pin_memory(), torch.empty((cap, 3)).pin_memory(), torch.empty(cap).pin_memory(),
+                       torch.empty((cap, 6)).pin_memory(), torch.empty((cap, 45)).pin_memory()]
+            ctx.bind_output(l, *[b.numpy() for b in bufs[l]])
+        for rep in range(2):
+            ctx.build(*[p.numpy() for p in pinned], cluster_level=L)
+            for l in range(1, L + 1):
+                m = ctx.level_size(l)
+                assert m == want[l]["xyz"].shape[0], (mode, rep, l)
+                got = ctx.level(l, with_internal=True)
+                for k in got:
+                    assert np.array_equal(got[k], want[l][k], equal_nan=True), (mode, rep, l, k)
+                for k, b in zip(("xyz", "colors", "opacity", "cov6", "sh"), bufs[l]):
+                    assert np.array_equal(b.numpy()[:m], want[l][k], equal_nan=True), f"bound output differs: mode {mode} level {l} {k}"
+            assert [ctx.step_stats(l)["n_dropped"] for l in range(L)] == dropped
