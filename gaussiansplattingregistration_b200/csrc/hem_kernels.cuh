@@ -1476,7 +1476,7 @@ k_moments(MomArgs A)
                 float gv[MOM_U], vs[NSH][MOM_U], wc[MOM_U];
 #pragma unroll
                 for (int u = 0; u < MOM_U; ++u) {
-                    const int c = min(g + u, cnt - 1);
+                    const int c = g + u;                  // <= 31; lanes past the window's last pair hold row 0 and weight 0
                     const uint32_t cc = __shfl_sync(full, ch, c);
                     wc[u] = __shfl_sync(full, w, c);
                     gv[u] = DO_GEO ? geof[16 * (size_t)cc + j] : 0.0f;
