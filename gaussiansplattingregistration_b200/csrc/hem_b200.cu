@@ -813,12 +813,23 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             return cub::DeviceRadixSort::SortPairs(t, b, ctx->key.as<uint32_t>(), ctx->key2.as<uint32_t>(),
                                                    ctx->val.as<uint32_t>(), ctx->val2.as<uint32_t>(), (int)n, 0, kbits, st);
         }));
+        // the thread that places a parent into the planes also writes its gate record (radius, rank, inverse covariance,
+        // cell box): parents are the slots [n - np, n).  Ellipsoid boxes only while the certified pre-test is active and
+        // every component of the level can be pre-tested.
+        CKR(ensure(ctx, PTAB, np * 8));
+        CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
+        const float kthr_ = distance_delta * distance_delta * 0.5f;
+        const bool pretest = ctx->smd_prefilter && kthr_ <= 1e4f;
+        const float s_box = (ctx->tight_box && pretest && ps.n_uncert == 0) ? (2.0f * kthr_ + 0.5f) / 0.99f * 1.001f : 0.0f;
+        S.tight = s_box > 0.0f;
+        CKR(join1());       // parent ranks (second stream)
         pdl(k_sorted_gather, blocks_for(n, 256), 256, 0, st)(geo, ctx->key2.as<uint32_t>(), ctx->val2.as<uint32_t>(), n,
                                                              2u * ncell, ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
                                                              ctx->sp2.as<float4>(), ctx->sp3.as<float4>(),
-                                                             ctx->cell_start.as<uint32_t>());
+                                                             ctx->cell_start.as<uint32_t>(), (uint32_t)(n - np),
+                                                             ctx->prank.as<uint32_t>(), RAD.as<float>(), SAFE.as<uint8_t>(), g, s_box,
+                                                             PTAB.as<uint2>(), ctx->pinfo.as<float4>());
         CK(cudaGetLastError()); ctx->n_launches++;
-        CKR(join1());
         if (ctx->timing == 1) CK(cudaEventRecord(ev[EV_GRID], st));
 
         // ---- S3 gate ----------------------------------------------------------------------------
@@ -832,18 +843,6 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         S.n_parents_local = my_np; S.shards = G;
         CKR(ensure(ctx, ctx->pair_off, (np + 1) * 4));
         CKR(ensure(ctx, ctx->pair_off_s, (np + 1) * 4));
-        CKR(ensure(ctx, PTAB, np * 8));
-        CKR(ensure(ctx, ctx->pinfo, (size_t)np * PINFO_F4 * 16));
-        // ellipsoid boxes (k_ptab): only while the certified pre-test is active and every component can be pre-tested
-        const float kthr_ = distance_delta * distance_delta * 0.5f;
-        const bool pretest = ctx->smd_prefilter && kthr_ <= 1e4f;
-        const float s_box = (ctx->tight_box && pretest && ps.n_uncert == 0) ? (2.0f * kthr_ + 0.5f) / 0.99f * 1.001f : 0.0f;
-        S.tight = s_box > 0.0f;
-        pdl(k_ptab, blocks_for(np, 256), 256, 0, st)((uint32_t)(n - np), ctx->sp0.as<float4>(), ctx->sp1.as<float4>(),
-                                                     ctx->sp2.as<float4>(), ctx->sp3.as<float4>(), ctx->prank.as<uint32_t>(),
-                                                     RAD.as<float>(), SAFE.as<uint8_t>(), geo, g, (int)np, s_box, PTAB.as<uint2>(),
-                                                     ctx->pinfo.as<float4>());
-        CK(cudaGetLastError()); ctx->n_launches++;
         size_t pool_cap = std::max<size_t>(std::max<size_t>(ctx->pool.cap / 8, ctx->pool_min), std::max<size_t>((size_t)8 * n / G, 1 << 16));
         unsigned long long nchunks = 0;
         // Single GPU, claim-table regime: nothing between the gate and the end of the step needs a size on

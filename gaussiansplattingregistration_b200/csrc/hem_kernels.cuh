@@ -5,7 +5,7 @@
 //   S1  k_prep (level 0) / k_finish of the previous step (levels >= 1)
 //                         parent radius, certificates, bbox / radius statistics     mixture.cpp:70-95
 //       k_boxhist         percentile box of the level-0 means (grid extent only)
-//   S2  k_cellkey + radix sort + k_sorted_gather + k_ptab   uniform grid            pointindex.cpp:55-108
+//   S2  k_cellkey + radix sort + k_sorted_gather (+ per-parent gate records)   uniform grid   pointindex.cpp:55-108
 //   S3  k_gate            radius / colour / KLD / parent-exclusion gates,           mixture.cpp:106-164
 //                         likelihood wL, pooled pair emission
 //       k_chunk_copy      pool -> cell-order CSR (+ claim-table insertion on one GPU)
@@ -493,10 +493,59 @@ __global__ void k_cellkey(const float4* __restrict__ geo, int64_t n, GridP g, ui
     val[i] = (uint32_t)i;
 }
 
+// conservative cell box of a parent's search sphere along one axis (DESIGN.md "grid range")
+__device__ __forceinline__ void cell_range(float q, float rr, float o, float inv_h, int g, int& lo, int& hi)
+{
+    const float pad = (fabsf(q) + rr) * 2.4e-7f;
+    lo = cell_axis(q - (rr + pad), o, inv_h, g);
+    hi = cell_axis(q + (rr + pad), o, inv_h, g);
+}
+
+// Per-parent record the gate starts from (7 float4 at cell-order position t), written by the thread that places the
+// parent into the cell-sorted planes: the parent's four plane rows, radius, weight, rank, index, FP32 inverse
+// covariance and its cell box - the sphere's, or the Mahalanobis ellipsoid's for certified parents (see `s_box`).
+constexpr int PINFO_F4 = 7;
+__device__ __forceinline__ void ptab_record(int t, uint32_t s, float4 p0, float4 p1, float4 p2, float4 p3, float weight,
+                                            uint32_t srank, float rad, uint32_t safe, const GridP& g, float s_box,
+                                            uint2* __restrict__ ptab, float4* __restrict__ pinfo)
+{
+    ptab[t] = make_uint2(s, srank);
+    const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
+    const Sym3 ip = inverse_sym3(pc, p3.z);
+    int y0 = 0, y1 = 0, z0 = 0, z1 = 0;
+    float hx = __uint_as_float(0x7f800000u);          // half-extent of the search box along x (+inf: the sphere's chord decides)
+    if (rad > 0.0f) {
+        const float rr = rad * 1.00001f;
+        float ry = rr, rz = rr;
+        // Ellipsoid box (s_box > 0: no component of the level is uncertified, and this parent is certified).  The
+        // certified pre-test (hem_math.cuh) rejects every candidate whose squared Mahalanobis distance exceeds
+        // 2*kthr + 0.5 in FP32; with d'P^-1 d >= d_i^2 / P_ii that is every candidate outside the axis-aligned box of
+        // the ellipsoid d'P^-1 d <= s_box, s_box = (2*kthr + 0.5) / 0.99 * 1.001 (the certificate bounds the FP32 value
+        // from below by 0.99 of the exact one).  Searching sphere-box INTERSECT ellipsoid-box leaves membership untouched.
+        if (s_box > 0.0f && safe) {
+            hx = sqrtf(s_box * p2.x) * 1.0001f;
+            ry = fminf(rr, sqrtf(s_box * p2.w) * 1.0001f);
+            rz = fminf(rr, sqrtf(s_box * p3.y) * 1.0001f);
+        }
+        cell_range(p0.y, ry, g.oy, g.inv_h, g.gy, y0, y1);
+        cell_range(p0.z, rz, g.oz, g.inv_h, g.gz, z0, z1);
+    }
+    float4* o = pinfo + (size_t)t * PINFO_F4;
+    o[0] = p0; o[1] = p1; o[2] = p2; o[3] = make_float4(p3.x, p3.y, p3.z, hx);
+    o[4] = make_float4(rad, weight, __uint_as_float(srank | (safe << 31)), __uint_as_float(s));
+    o[5] = make_float4(ip.e00, ip.e01, ip.e02, ip.e11);
+    o[6] = make_float4(ip.e12, ip.e22, __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
+                       __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
+}
+
 __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* __restrict__ skey,
                                 const uint32_t* __restrict__ sval, int64_t n, uint32_t ncell,
                                 float4* __restrict__ sp0, float4* __restrict__ sp1, float4* __restrict__ sp2,
-                                float4* __restrict__ sp3, uint32_t* __restrict__ cell_start)
+                                float4* __restrict__ sp3, uint32_t* __restrict__ cell_start,
+                                // parents (slots [nc, n), whole warps of them but one): their gate records
+                                uint32_t nc, const uint32_t* __restrict__ prank, const float* __restrict__ radius,
+                                const uint8_t* __restrict__ psafe, GridP g, float s_box, uint2* __restrict__ ptab,
+                                float4* __restrict__ pinfo)
 {
     pdl_enter();
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,10 +553,15 @@ __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* 
     uint32_t i = sval[j], key = skey[j];
     float4 q0 = geo[4 * (size_t)i], q1 = geo[4 * (size_t)i + 1], q2 = geo[4 * (size_t)i + 2], q3 = geo[4 * (size_t)i + 3];
     uint32_t flag = __float_as_uint(q3.w) & 1u;
-    sp0[j] = make_float4(q0.x, q0.y, q0.z, __uint_as_float(i | (flag << 31)));
-    sp1[j] = make_float4(q3.x, q3.y, q3.z, q2.z);
+    const float4 r0 = make_float4(q0.x, q0.y, q0.z, __uint_as_float(i | (flag << 31)));
+    const float4 r1 = make_float4(q3.x, q3.y, q3.z, q2.z);
+    const float4 r3 = make_float4(q2.x, q2.y, q2.w, __uint_as_float((__float_as_uint(q3.w) >> 1) & 1u));
+    sp0[j] = r0;
+    sp1[j] = r1;
     sp2[j] = q1;
-    sp3[j] = make_float4(q2.x, q2.y, q2.w, __uint_as_float((__float_as_uint(q3.w) >> 1) & 1u));
+    sp3[j] = r3;
+    if (pinfo && j >= (int64_t)nc)
+        ptab_record((int)(j - (int64_t)nc), i, r0, r1, q1, r3, q0.w, prank[i], radius[i], (uint32_t)psafe[i], g, s_box, ptab, pinfo);
     // segment offsets: cell_start[c] = first slot whose key >= c
     uint32_t lo = (j == 0) ? 0u : skey[j - 1] + 1u;
     if (j == 0 || key != skey[j - 1])
@@ -540,13 +594,12 @@ __device__ __forceinline__ bool pool_overflowed(const unsigned long long* counte
     return (counters[C_POOL] & ((1ull << POOL_BITS) - 1ull)) > pool_cap;
 }
 
-// per-parent record in cell order, built once per step by k_ptab so that a gate warp starts
+// per-parent record in cell order, built once per step (ptab_record, in k_sorted_gather) so that a gate warp starts
 // from ONE contiguous 80-byte read instead of a chain of dependent gathers
 //   [0..3] = sp0..sp3 of the parent's slot,
 //   [4] = (radius, weight, bits(canonical rank | certified << 31), bits(canonical index))
 //   [5] = (ip00, ip01, ip02, ip11)   the FP32 inverse covariance of the KLD gate, computed once per
 //   [6] = (ip12, ip22, bits(y0 | y1 << 16), bits(z0 | z1 << 16))   parent by a THREAD instead of a warp
-constexpr int PINFO_F4 = 7;
 
 struct GateArgs {
     const float4* sp0; const float4* sp1; const float4* sp2; const float4* sp3;
@@ -578,59 +631,6 @@ struct GateArgs {
 };
 
 constexpr int GATE_SEG_ROWS = 64;            // rows of cells per work item of the heavy gate
-
-// conservative cell box of a parent's search sphere along one axis (DESIGN.md "grid range")
-__device__ __forceinline__ void cell_range(float q, float rr, float o, float inv_h, int g, int& lo, int& hi)
-{
-    const float pad = (fabsf(q) + rr) * 2.4e-7f;
-    lo = cell_axis(q - (rr + pad), o, inv_h, g);
-    hi = cell_axis(q + (rr + pad), o, inv_h, g);
-}
-
-__global__ void k_ptab(uint32_t nc, const float4* __restrict__ sp0,
-                       const float4* __restrict__ sp1, const float4* __restrict__ sp2,
-                       const float4* __restrict__ sp3, const uint32_t* __restrict__ prank,
-                       const float* __restrict__ radius, const uint8_t* __restrict__ psafe,
-                       const float4* __restrict__ geo, GridP g, int np, float s_box, uint2* __restrict__ ptab,
-                       float4* __restrict__ pinfo)
-{
-    pdl_enter();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= np) return;
-    const uint32_t pj = nc + (uint32_t)t;           // parents follow the nc non-parents, in cell order
-    const float4 p0 = sp0[pj], p2 = sp2[pj], p3 = sp3[pj];
-    const uint32_t s = __float_as_uint(p0.w) & 0x7fffffffu;
-    const uint32_t srank = prank[s];
-    const float rad = radius[s];
-    ptab[t] = make_uint2(s, srank);
-    const Sym3 pc = { p2.x, p2.y, p2.z, p2.w, p3.x, p3.y };
-    const Sym3 ip = inverse_sym3(pc, p3.z);
-    int y0 = 0, y1 = 0, z0 = 0, z1 = 0;
-    float hx = __uint_as_float(0x7f800000u);          // half-extent of the search box along x (+inf: the sphere's chord decides)
-    if (rad > 0.0f) {
-        const float rr = rad * 1.00001f;
-        float ry = rr, rz = rr;
-        // Ellipsoid box (s_box > 0: no component of the level is uncertified, and this parent is certified).  The
-        // certified pre-test (hem_math.cuh) rejects every candidate whose squared Mahalanobis distance exceeds
-        // 2*kthr + 0.5 in FP32; with d'P^-1 d >= d_i^2 / P_ii that is every candidate outside the axis-aligned box of
-        // the ellipsoid d'P^-1 d <= s_box, s_box = (2*kthr + 0.5) / 0.99 * 1.001 (the certificate bounds the FP32 value
-        // from below by 0.99 of the exact one).  Searching sphere-box INTERSECT ellipsoid-box leaves membership untouched.
-        if (s_box > 0.0f && psafe[s]) {
-            hx = sqrtf(s_box * p2.x) * 1.0001f;
-            ry = fminf(rr, sqrtf(s_box * p2.w) * 1.0001f);
-            rz = fminf(rr, sqrtf(s_box * p3.y) * 1.0001f);
-        }
-        cell_range(p0.y, ry, g.oy, g.inv_h, g.gy, y0, y1);
-        cell_range(p0.z, rz, g.oz, g.inv_h, g.gz, z0, z1);
-    }
-    float4* o = pinfo + (size_t)t * PINFO_F4;
-    o[0] = p0; o[1] = sp1[pj]; o[2] = p2; o[3] = make_float4(p3.x, p3.y, p3.z, hx);
-    o[4] = make_float4(rad, geo[4 * (size_t)s].w, __uint_as_float(srank | ((uint32_t)psafe[s] << 31)),
-                       __uint_as_float(s));
-    o[5] = make_float4(ip.e00, ip.e01, ip.e02, ip.e11);
-    o[6] = make_float4(ip.e12, ip.e22, __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
-                       __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
-}
 
 // HEAVY = false: the ordinary kernel (one warp per parent, tickets of A.tb parents).
 // HEAVY = true : only the parents listed in seg_info; one ticket = one segment of GATE_SEG_ROWS rows of one parent.
@@ -859,7 +859,7 @@ k_gate(GateArgs A)
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
             const float inv_ny = 1.0f / (float)ny;
-            // x range of the ellipsoid box (k_ptab; the whole grid when the parent searches its sphere)
+            // x range of the ellipsoid box (ptab_record; the whole grid when the parent searches its sphere)
             int xlo = 0, xhi = A.g.gx - 1;
             if (p3.w < 3.0e38f) cell_range(p0.x, p3.w, A.g.ox, A.g.inv_h, A.g.gx, xlo, xhi);
             if (!HEAVY) {
