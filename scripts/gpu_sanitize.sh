@@ -27,6 +27,19 @@ print("heavy gate sizes", [ctx3.level_size(l) for l in range(3)], float(m["_rota
 ctx3.set_option("overlap", 0)
 ctx3.build(*c.arrays(), cluster_level=2)
 print("no-overlap sizes", [ctx3.level_size(l) for l in range(3)])
+# geometry-first pipeline forced on every level: pinned host inputs, bound pinned outputs (SH passes, stash, download stream)
+import torch
+h = synth(40000, seed=11, density=5000.0)
+pin = [torch.from_numpy(x).pin_memory() for x in h.arrays()]
+ctx4 = HemContext(0, 7)
+ctx4.set_option("geo_first", 2)
+outs = {}
+for l in (1, 2, 3):
+    outs[l] = [torch.empty((h.n, 3)).pin_memory(), torch.empty((h.n, 3)).pin_memory(), torch.empty(h.n).pin_memory(),
+               torch.empty((h.n, 6)).pin_memory(), torch.empty((h.n, 45)).pin_memory()]
+    ctx4.bind_output(l, *[b.numpy() for b in outs[l]])
+ctx4.build(*[p.numpy() for p in pin], cluster_level=3)
+print("geo-first sizes", [ctx4.level_size(l) for l in range(4)], float(outs[3][4][:ctx4.level_size(3)].sum()))
 # ICP consumer: two small pyramids, coarse-to-fine; plus host arrays with correspondences and a fringe (no match) part
 from gaussiansplattingregistration_b200.synth import rigid_copy
 a = synth(20000, seed=8, density=5000.0)
