@@ -504,7 +504,7 @@ __device__ __forceinline__ void cell_range(float q, float rr, float o, float inv
 // Per-parent record the gate starts from (7 float4 at cell-order position t), written by the thread that places the
 // parent into the cell-sorted planes: the parent's four plane rows, radius, weight, rank, index, FP32 inverse
 // covariance and its cell box - the sphere's, or the Mahalanobis ellipsoid's for certified parents (see `s_box`).
-constexpr int PINFO_F4 = 7;
+constexpr int PINFO_F4 = 8;
 __device__ __forceinline__ void ptab_record(int t, uint32_t s, float4 p0, float4 p1, float4 p2, float4 p3, float weight,
                                             uint32_t srank, float rad, uint32_t safe, const GridP& g, float s_box,
                                             uint2* __restrict__ ptab, float4* __restrict__ pinfo)
@@ -536,6 +536,12 @@ __device__ __forceinline__ void ptab_record(int t, uint32_t s, float4 p0, float4
     o[5] = make_float4(ip.e00, ip.e01, ip.e02, ip.e11);
     o[6] = make_float4(ip.e12, ip.e22, __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
                        __uint_as_float((uint32_t)z0 | ((uint32_t)z1 << 16)));
+    // what every lane of the gate warp would otherwise recompute per parent: x range of the ellipsoid box (the whole
+    // grid when the parent searches its sphere), 1 / rows-per-z-slice of its box, squared padded radius
+    int xlo = 0, xhi = g.gx - 1;
+    if (hx < 3.0e38f) cell_range(p0.x, hx, g.ox, g.inv_h, g.gx, xlo, xhi);
+    const float rr = rad * 1.00001f;
+    o[7] = make_float4(__int_as_float(xlo), __int_as_float(xhi), 1.0f / (float)(y1 - y0 + 1), rr * rr);
 }
 
 __global__ void k_sorted_gather(const float4* __restrict__ geo, const uint32_t* __restrict__ skey,
@@ -600,6 +606,7 @@ __device__ __forceinline__ bool pool_overflowed(const unsigned long long* counte
 //   [4] = (radius, weight, bits(canonical rank | certified << 31), bits(canonical index))
 //   [5] = (ip00, ip01, ip02, ip11)   the FP32 inverse covariance of the KLD gate, computed once per
 //   [6] = (ip12, ip22, bits(y0 | y1 << 16), bits(z0 | z1 << 16))   parent by a THREAD instead of a warp
+//   [7] = (bits(xlo), bits(xhi), 1 / (y1 - y0 + 1), (radius * 1.00001)^2)
 
 struct GateArgs {
     const float4* sp0; const float4* sp1; const float4* sp2; const float4* sp3;
@@ -834,7 +841,7 @@ k_gate(GateArgs A)
       for (int t = tfirst; t < tlast; ++t) {
 
         const float4* pi = A.pinfo + (size_t)t * PINFO_F4;
-        const float4 p0 = pi[0], p1 = pi[1], p3 = pi[3], p4 = pi[4], p5 = pi[5], p6 = pi[6];
+        const float4 p0 = pi[0], p1 = pi[1], p3 = pi[3], p4 = pi[4], p5 = pi[5], p6 = pi[6], p7 = pi[7];
         const float rad = p4.x;
         const float r2 = fm(rad, rad);
 
@@ -852,16 +859,14 @@ k_gate(GateArgs A)
         if (rad > 0.0f) {        // NaN / zero radius: no child can pass `d2 < r*r` (pointindex.cpp:138)
             // conservative cell box (DESIGN.md "grid range"): the float test can only pass for
             // |d| <= rad*(1+5*2^-24) per axis; pads cover the rounding of the range ends themselves
-            const float rr = rad * 1.00001f;
-            const float rr2 = rr * rr;
+            const float rr2 = p7.w;
             const int y0 = (int)(__float_as_uint(p6.z) & 0xffffu), y1 = (int)(__float_as_uint(p6.z) >> 16);
             const int z0 = (int)(__float_as_uint(p6.w) & 0xffffu), z1 = (int)(__float_as_uint(p6.w) >> 16);
             const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
             const int nrows = ny * nz;
-            const float inv_ny = 1.0f / (float)ny;
+            const float inv_ny = p7.z;
             // x range of the ellipsoid box (ptab_record; the whole grid when the parent searches its sphere)
-            int xlo = 0, xhi = A.g.gx - 1;
-            if (p3.w < 3.0e38f) cell_range(p0.x, p3.w, A.g.ox, A.g.inv_h, A.g.gx, xlo, xhi);
+            const int xlo = __float_as_int(p7.x), xhi = __float_as_int(p7.y);
             if (!HEAVY) {
                 if (A.row_report > 0 && nrows > A.row_report && lane == 0) atomicAdd(A.n_heavy_gate, 1u);
                 if (A.row_defer > 0 && nrows > A.row_defer) {          // uniform: left to k_gate<true>

@@ -10,3 +10,6 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1
 bash scripts/gpu_prof.sh 3m
 timeout 900 bash scripts/gpu_sanitize.sh 2>&1 | tee gpurun_out/sanitize.log | tail -30
 timeout 600 python bench.py --workload 10m --steps 5 --warmup 3 --skip-e2e --no-cpu-baseline --no-extra 2>&1 | tail -1 | tee gpurun_out/bench10m_n1.json | cut -c1-200
+timeout 600 python bench.py --workload 1m --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | tail -1 | tee gpurun_out/bench1m_n1.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('1M x 5: value %.3e (%.3f ms)  e2e %.3e (%.2f ms)' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step']))"
