@@ -156,6 +156,9 @@ class HemContext:
         self.close()
 
     def set_option(self, name: str, value: float):
+        """hem_set_option (include/hem_b200.h lists every option): e.g. "timing" (1: events around every stage, 2: level
+        and hot kernels only), "keep_pairs", "geo_first" (host SH input: geometry rows first, SH passes once the upload has
+        landed), "overlap", "poll_sync", "tight_box", "heavy_rows", "shard_min_n".  Results never depend on them."""
         self._check(self._lib.hem_set_option(self._h, name.encode(), float(value)))
 
     def set_stream(self, stream_handle: int | None):
