@@ -91,6 +91,8 @@ struct hem_ctx {
     int64_t prep_n = 0;
     Ctl prep_stats;
     bool dense_hint = false;       // last step had more than 4 accepted pairs per component (or its claim table overflowed)
+    std::vector<int64_t> claims_failed_n;      // per level: size of the level whose claim summation gave up in an earlier build
+                                               // (a build of a same-sized level starts on the sort path instead of redoing the step)
     int redo_depth = 0;            // guards the redo recursion of run_step
     size_t pool_min = 0;           // pair pool size learned from an overflow
     // robust grid box of the current build (percentile range of the level-0 means, see k_boxhist)
@@ -848,6 +850,7 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
         // Single GPU, claim-table regime: nothing between the gate and the end of the step needs a size on
         // the host (launches are sized by capacities, counts are read on the device), so the step runs with
         // ONE host sync at its end; a pool overflow is detected there and the step is redone with a larger pool.
+        if (ctx->sumlw_mode == 0 && (size_t)l < ctx->claims_failed_n.size() && ctx->claims_failed_n[l] == n) ctx->dense_hint = true;
         const bool guess_claims = ctx->sumlw_mode == 2 || (ctx->sumlw_mode == 0 && !ctx->dense_hint);
         const bool fast = (G == 1) && !ctx->keep_pairs && guess_claims;
         size_t chunk_cap_used = 0;
@@ -1208,7 +1211,11 @@ int run_step(hem_ctx* ctx, int l, float hem_reduction, float distance_delta, flo
             // nothing was corrupted (pool writes are guarded, the claim summation bailed out): redo the step
             // with a larger pool / through the sort path; the carried prep of THIS level is still intact
             if (overflow) ctx->pool_min = (size_t)pairs + (size_t)pairs / 4 + 1024;
-            if (claims_failed) ctx->dense_hint = true;
+            if (claims_failed) {
+                ctx->dense_hint = true;
+                if (ctx->claims_failed_n.size() <= (size_t)l) ctx->claims_failed_n.resize((size_t)l + 1, -1);
+                ctx->claims_failed_n[l] = n;
+            }
             ctx->prep_valid = carried;
             ctx->prep_level = l; ctx->prep_n = n; ctx->prep_stats = ps;
             if (++ctx->redo_depth > 4) { ctx->redo_depth = 0; ctx->err = "clustering step did not settle after 4 redos (pool / claim table)"; return HEM_ERR_STATE; }

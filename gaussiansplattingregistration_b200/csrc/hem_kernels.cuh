@@ -1281,7 +1281,9 @@ k_sumlw_claims(const uint32_t* __restrict__ cnt_c, const uint2* __restrict__ cla
     if (m > (uint32_t)(CLAIM_K1 + CLAIM_K)) {
         // beyond both tiers: the rest sits in the global overflow list, which the child scans
         const unsigned long long nov = counters[C_OVF];
-        if (nov > ovf_limit) {          // dense regime reached the claim table: give up, the host redoes the step by sorting
+        // dense regime reached the claim table - too many overflow entries, or a hub child whose scan of the list would
+        // be a long serial loop of ONE thread (m passes over it): give up, the host redoes the step by sorting
+        if (nov > ovf_limit || (ovf_limit != ~0ull && (unsigned long long)m * (nov + (unsigned long long)(CLAIM_K1 + CLAIM_K)) > (1ull << 16))) {
             counters[C_FAIL] = 1ull;
         } else {
             long long last = -1;
