@@ -105,8 +105,8 @@ struct hem_ctx {
     // the same for the gate, by rows of cells of the search box: a parent whose box has more rows than
     // max(heavy_rows, heavy_rows_rel x the box of a parent of geometric-mean radius) is scanned by the grid in
     // segments of GATE_SEG_ROWS rows instead of by one warp (heavy_rows = 0: never)
-    int heavy_rows = 1024;
-    double heavy_rows_rel = 16.0;
+    int heavy_rows = 256;          // (1024 / 16 left parents of a few hundred rows to one warp: heavy-tailed stress cloud 31 -> 22 ms,
+    double heavy_rows_rel = 8.0;   //  ordinary pyramids unchanged)
     bool heavy_gate_hint = false;
     double cell_scale = 0.55;
     double cell_occupancy = 1.3;   // lower bound of the cell edge in units of the mean component spacing

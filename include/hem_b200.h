@@ -80,7 +80,7 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *   "poll_sync"   1 (default) -> the one host wait per level polls a mapped word instead of synchronising the stream
  *   "heavy_rows"  a parent whose search box has more rows of cells than max(heavy_rows, heavy_rows_rel x the box of a
  *                 parent of geometric-mean radius) is scanned by the whole grid in segments instead of by one warp
- *                 (defaults 128 and 16; heavy_rows = 0: never; single GPU)
+ *                 (defaults 256 and 8; heavy_rows = 0: never; single GPU)
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
  *                 being sharded (default 2000000; the per-level exchanges cost more than they save below it)
  *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own
