@@ -78,9 +78,9 @@ int hem_set_stream(hem_ctx* ctx, void* stream);
  *                 of those levels once the rows have landed; 0 -> every step waits for the SH rows it reads; 2 -> defer
  *                 on every level of such a build (tests).  Results are bit-identical in all three.
  *   "poll_sync"   1 (default) -> the one host wait per level polls a mapped word instead of synchronising the stream
- *   "heavy_rows"  a parent whose search box has more rows of cells than max(heavy_rows, heavy_rows_rel x the box of a
- *                 parent of geometric-mean radius) is scanned by the whole grid in segments instead of by one warp
- *                 (defaults 256 and 8; heavy_rows = 0: never; single GPU)
+ *   "heavy_rows", "heavy_rows_rel"  a parent whose search box has more rows of cells than max(heavy_rows,
+ *                 heavy_rows_rel x the box of a parent of geometric-mean radius) is scanned by the whole grid in
+ *                 segments instead of by one warp (defaults 256 and 8; heavy_rows = 0: never; single GPU)
  *   "shard_min_n" multi-GPU: levels with fewer components are built whole on every rank instead of
  *                 being sharded (default 2000000; the per-level exchanges cost more than they save below it)
  *   "shard_upload" multi-GPU, host inputs: 1 (default) -> every rank uploads 1/world of each array over its own

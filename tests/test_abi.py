@@ -131,3 +131,20 @@ def test_registration_host_side_types():
         reg.do_icp_registration(PC(), PC(), np.eye(4), reg.LocalRegistrationParams(registration_type=reg.LocalRegistrationType.ICP_General))
     with pytest.raises(ValueError, match="mixture levels do not match"):
         reg.register_gaussian_clouds((), (), None, [1.0], [5])
+
+
+def test_options_and_statistics_are_documented():
+    """Every option hem_set_option accepts is described in include/hem_b200.h, and the step statistics have the same
+    length in the header, the ctypes binding and the Python names."""
+    from gaussiansplattingregistration_b200 import _capi
+    from gaussiansplattingregistration_b200.hem import STAT_NAMES
+    header = open(HEADER).read()
+    host = open(os.path.join(ROOT, "gaussiansplattingregistration_b200", "csrc", "hem_b200.cu")).read()
+    body = host[host.index("int hem_set_option("):]
+    body = body[:body.index("\n}\n")]
+    options = set(re.findall(r'k == "([a-z0-9_]+)"', body))
+    assert len(options) >= 15
+    undocumented = sorted(o for o in options if f'"{o}"' not in header)
+    assert not undocumented, f"options missing from include/hem_b200.h: {undocumented}"
+    m = re.search(r"#define\s+HEM_STEP_STATS_LEN\s+(\d+)", header)
+    assert m and int(m.group(1)) == _capi.STEP_STATS_LEN == len(STAT_NAMES)
